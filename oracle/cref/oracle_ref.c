@@ -1,0 +1,546 @@
+/*
+ * oracle_ref.c -- plain-C CPU restatement of the ark-crypto-primitives hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under crypto_primitives_b200/ or include/ may
+ * link or call this file; only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs do, as the checker and the timed CPU baseline.
+ *
+ * It is a RESTATEMENT ("port"), not the reference: the reference is Rust and its
+ * arithmetic lives in ark-ff / ark-ec ^0.4, which are not under /root/reference and
+ * cannot be built here (no rustc/cargo in this image).  Each function cites the
+ * reference lines it follows (R = /root/reference/crypto-primitives/src).  It keeps
+ * the reference's algorithmic shape on purpose -- dense t x t MDS every round,
+ * generic square-and-multiply x^alpha, one hash at a time, per-level barriers --
+ * because it doubles as the timed "C restatement of the reference CPU path".
+ * Data parallelism mirrors the reference's rayon `parallel` feature
+ * (R/merkle_tree/mod.rs:417,458,494) with pthreads.
+ *
+ * Interchange: field elements are 4 x u64 little-endian limbs in Montgomery form,
+ * R = 2^256, fully reduced (what ark-ff's Fp<MontBackend<_,4>,4> holds).
+ *
+ * Pinning: Poseidon results are pinned by the reference KATs through the Python
+ * oracle (tests/test_oracle_*.py check C == Python == KAT).  Pedersen / Merkle:
+ * PARITY UNPINNED (no golden vectors exist in the reference).
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned __int128 u128;
+typedef uint64_t u64;
+
+typedef struct { u64 l[4]; } fe;
+
+typedef struct {
+    u64 p[4];
+    u64 ninv;      /* -p^{-1} mod 2^64 */
+    fe one;        /* R mod p */
+    fe r2;         /* R^2 mod p */
+} field_t;
+
+/* ---------------------------------------------------------------- field */
+
+static int ge4(const u64 a[4], const u64 b[4]) {
+    for (int i = 3; i >= 0; i--) {
+        if (a[i] > b[i]) return 1;
+        if (a[i] < b[i]) return 0;
+    }
+    return 1;
+}
+
+static u64 sub4(u64 r[4], const u64 a[4], const u64 b[4]) {
+    u64 borrow = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 d = (u128)a[i] - b[i] - borrow;
+        r[i] = (u64)d;
+        borrow = (u64)(d >> 64) & 1;
+    }
+    return borrow;
+}
+
+static u64 add4(u64 r[4], const u64 a[4], const u64 b[4]) {
+    u64 c = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 s = (u128)a[i] + b[i] + c;
+        r[i] = (u64)s;
+        c = (u64)(s >> 64);
+    }
+    return c;
+}
+
+static void fe_add(const field_t *F, fe *r, const fe *a, const fe *b) {
+    u64 t[4];
+    u64 c = add4(t, a->l, b->l);
+    if (c || ge4(t, F->p)) sub4(t, t, F->p);
+    memcpy(r->l, t, 32);
+}
+
+static void fe_sub(const field_t *F, fe *r, const fe *a, const fe *b) {
+    u64 t[4];
+    if (sub4(t, a->l, b->l)) add4(t, t, F->p);
+    memcpy(r->l, t, 32);
+}
+
+/* Montgomery product a*b/R mod p (CIOS, 64-bit limbs). */
+static void fe_mul(const field_t *F, fe *r, const fe *a, const fe *b) {
+    u64 t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        u64 c = 0;
+        for (int j = 0; j < 4; j++) {
+            u128 s = (u128)a->l[j] * b->l[i] + t[j] + c;
+            t[j] = (u64)s;
+            c = (u64)(s >> 64);
+        }
+        u128 s = (u128)t[4] + c;
+        t[4] = (u64)s;
+        t[5] = (u64)(s >> 64);
+        u64 m = t[0] * F->ninv;
+        s = (u128)m * F->p[0] + t[0];
+        c = (u64)(s >> 64);
+        for (int j = 1; j < 4; j++) {
+            s = (u128)m * F->p[j] + t[j] + c;
+            t[j - 1] = (u64)s;
+            c = (u64)(s >> 64);
+        }
+        s = (u128)t[4] + c;
+        t[3] = (u64)s;
+        t[4] = t[5] + (u64)(s >> 64);
+    }
+    if (t[4] || ge4(t, F->p)) sub4(t, t, F->p);
+    memcpy(r->l, t, 32);
+}
+
+/* x^e, left-to-right square-and-multiply over the exponent bits (ark-ff Field::pow, dep). */
+static void fe_pow_u64(const field_t *F, fe *r, const fe *x, u64 e) {
+    fe acc = F->one;
+    int started = 0;
+    for (int i = 63; i >= 0; i--) {
+        if (started) fe_mul(F, &acc, &acc, &acc);
+        if ((e >> i) & 1) {
+            started = 1;
+            fe_mul(F, &acc, &acc, x);
+        }
+    }
+    *r = acc;
+}
+
+static void fe_pow4(const field_t *F, fe *r, const fe *x, const u64 e[4]) {
+    fe acc = F->one;
+    for (int i = 255; i >= 0; i--) {
+        fe_mul(F, &acc, &acc, &acc);
+        if ((e[i / 64] >> (i % 64)) & 1) fe_mul(F, &acc, &acc, x);
+    }
+    *r = acc;
+}
+
+static void fe_inv(const field_t *F, fe *r, const fe *x) {
+    u64 e[4], two[4] = {2, 0, 0, 0};
+    sub4(e, F->p, two);
+    fe_pow4(F, r, x, e);
+}
+
+int oref_field_init(field_t *F, const u64 p[4]) {
+    memcpy(F->p, p, 32);
+    u64 inv = 1;
+    for (int i = 0; i < 6; i++) inv *= 2 - p[0] * inv;   /* Newton: p^{-1} mod 2^64 */
+    F->ninv = (u64)0 - inv;
+    /* one = 2^256 mod p by doubling 1 256 times; r2 by 256 more doublings of one. */
+    fe x;
+    memset(&x, 0, sizeof x);
+    x.l[0] = 1;
+    for (int i = 0; i < 512; i++) {
+        u64 t[4];
+        u64 c = add4(t, x.l, x.l);
+        if (c || ge4(t, F->p)) sub4(t, t, F->p);
+        memcpy(x.l, t, 32);
+        if (i == 255) F->one = x;
+    }
+    F->r2 = x;
+    return 0;
+}
+
+field_t *oref_field_new(const u64 p[4]) {
+    field_t *F = (field_t *)calloc(1, sizeof *F);
+    oref_field_init(F, p);
+    return F;
+}
+void oref_field_free(field_t *F) { free(F); }
+
+/* canonical integer (4 LE limbs) <-> Montgomery */
+void oref_to_mont(const field_t *F, u64 *out, const u64 *in, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        fe a;
+        memcpy(a.l, in + 4 * i, 32);
+        if (ge4(a.l, F->p)) sub4(a.l, a.l, F->p);      /* inputs < 2^256 < 3p for our fields: loop */
+        while (ge4(a.l, F->p)) sub4(a.l, a.l, F->p);
+        fe_mul(F, &a, &a, &F->r2);
+        memcpy(out + 4 * i, a.l, 32);
+    }
+}
+
+void oref_from_mont(const field_t *F, u64 *out, const u64 *in, size_t n) {
+    fe one_plain = {{1, 0, 0, 0}};
+    for (size_t i = 0; i < n; i++) {
+        fe a;
+        memcpy(a.l, in + 4 * i, 32);
+        fe_mul(F, &a, &a, &one_plain);
+        memcpy(out + 4 * i, a.l, 32);
+    }
+}
+
+/* ---------------------------------------------------------------- parallel-for */
+
+typedef void (*range_fn)(void *ctx, size_t begin, size_t end);
+typedef struct { range_fn fn; void *ctx; size_t begin, end; } job_t;
+
+static void *job_main(void *arg) {
+    job_t *j = (job_t *)arg;
+    j->fn(j->ctx, j->begin, j->end);
+    return NULL;
+}
+
+/* One fork/join per call == one rayon barrier per tree level (R/merkle_tree/mod.rs:458,494). */
+static void parallel_for(size_t n, int threads, range_fn fn, void *ctx) {
+    if (threads < 1) threads = 1;
+    if ((size_t)threads > n) threads = n ? (int)n : 1;
+    if (threads == 1) { fn(ctx, 0, n); return; }
+    pthread_t *tid = (pthread_t *)malloc(sizeof(pthread_t) * threads);
+    job_t *jobs = (job_t *)malloc(sizeof(job_t) * threads);
+    size_t chunk = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; t++) {
+        size_t b = (size_t)t * chunk, e = b + chunk;
+        if (b > n) b = n;
+        if (e > n) e = n;
+        jobs[t] = (job_t){fn, ctx, b, e};
+        pthread_create(&tid[t], NULL, job_main, &jobs[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(tid[t], NULL);
+    free(tid);
+    free(jobs);
+}
+
+/* ---------------------------------------------------------------- Poseidon */
+
+#define MAX_T 16
+
+typedef struct {
+    field_t F;
+    int rate, capacity, full_rounds, partial_rounds;
+    u64 alpha;
+    fe *ark;   /* [(RF+RP)][t] */
+    fe *mds;   /* [t][t] */
+} poseidon_t;
+
+poseidon_t *oref_poseidon_new(const u64 p[4], int rate, int capacity, int full_rounds,
+                              int partial_rounds, u64 alpha, const u64 *ark_mont, const u64 *mds_mont) {
+    int t = rate + capacity;
+    if (t > MAX_T || t < 2) return NULL;
+    poseidon_t *P = (poseidon_t *)calloc(1, sizeof *P);
+    oref_field_init(&P->F, p);
+    P->rate = rate; P->capacity = capacity;
+    P->full_rounds = full_rounds; P->partial_rounds = partial_rounds; P->alpha = alpha;
+    size_t na = (size_t)(full_rounds + partial_rounds) * t, nm = (size_t)t * t;
+    P->ark = (fe *)malloc(na * sizeof(fe));
+    P->mds = (fe *)malloc(nm * sizeof(fe));
+    memcpy(P->ark, ark_mont, na * 32);
+    memcpy(P->mds, mds_mont, nm * 32);
+    return P;
+}
+
+void oref_poseidon_free(poseidon_t *P) {
+    if (!P) return;
+    free(P->ark); free(P->mds); free(P);
+}
+
+const field_t *oref_poseidon_field(const poseidon_t *P) { return &P->F; }
+
+/* PoseidonSponge::permute, R/sponge/poseidon/mod.rs:66-121: ark, s-box, dense MDS each round. */
+static void permute(const poseidon_t *P, fe *st) {
+    const field_t *F = &P->F;
+    int t = P->rate + P->capacity, half = P->full_rounds / 2;
+    fe nw[MAX_T];
+    for (int r = 0; r < P->full_rounds + P->partial_rounds; r++) {
+        for (int i = 0; i < t; i++) fe_add(F, &st[i], &st[i], &P->ark[r * t + i]);      /* :79-83 */
+        if (r < half || r >= half + P->partial_rounds) {                                   /* :66-77 */
+            for (int i = 0; i < t; i++) fe_pow_u64(F, &st[i], &st[i], P->alpha);
+        } else {
+            fe_pow_u64(F, &st[0], &st[0], P->alpha);
+        }
+        for (int i = 0; i < t; i++) {                                                      /* :85-96 */
+            fe cur;
+            memset(&cur, 0, sizeof cur);
+            for (int j = 0; j < t; j++) {
+                fe term;
+                fe_mul(F, &term, &st[j], &P->mds[i * t + j]);
+                fe_add(F, &cur, &cur, &term);
+            }
+            nw[i] = cur;
+        }
+        memcpy(st, nw, sizeof(fe) * t);
+    }
+}
+
+void oref_poseidon_permute(const poseidon_t *P, u64 *state_inout) {
+    permute(P, (fe *)state_inout);
+}
+
+/* crh::poseidon::CRH::evaluate (R/crh/poseidon/mod.rs:30-40): new sponge, absorb the whole
+ * input (absorb_internal, sponge/poseidon/mod.rs:124-153), squeeze one element (:323-345). */
+static void crh_one(const poseidon_t *P, const fe *in, size_t len, fe *out) {
+    const field_t *F = &P->F;
+    int t = P->rate + P->capacity;
+    fe st[MAX_T];
+    memset(st, 0, sizeof(fe) * t);
+    size_t pos = 0;
+    while (len - pos > (size_t)P->rate) {           /* more than `rate` remain: fill and permute */
+        for (int i = 0; i < P->rate; i++) fe_add(F, &st[P->capacity + i], &st[P->capacity + i], &in[pos + i]);
+        permute(P, st);
+        pos += P->rate;
+    }
+    for (size_t i = 0; pos + i < len; i++) fe_add(F, &st[P->capacity + i], &st[P->capacity + i], &in[pos + i]);
+    permute(P, st);                                 /* squeeze from Absorbing mode permutes once */
+    *out = st[P->capacity];
+}
+
+typedef struct { const poseidon_t *P; const fe *in; size_t len; size_t stride; fe *out; } crh_job;
+static void crh_range(void *c, size_t b, size_t e) {
+    crh_job *j = (crh_job *)c;
+    for (size_t i = b; i < e; i++) crh_one(j->P, j->in + i * j->stride, j->len, &j->out[i]);
+}
+
+/* n independent CRH evaluations, each over `len` elements (inputs contiguous, `len` apart). */
+void oref_poseidon_crh_batch(const poseidon_t *P, const u64 *in, size_t len, u64 *out, size_t n, int threads) {
+    crh_job j = {P, (const fe *)in, len, len, (fe *)out};
+    parallel_for(n, threads, crh_range, &j);
+}
+
+/* TwoToOneCRH::compress (R/crh/poseidon/mod.rs:66-79) over n (left,right) pairs. */
+void oref_poseidon_compress_batch(const poseidon_t *P, const u64 *pairs, u64 *out, size_t n, int threads) {
+    crh_job j = {P, (const fe *)pairs, 2, 2, (fe *)out};
+    parallel_for(n, threads, crh_range, &j);
+}
+
+/* MerkleTree::new with Poseidon leaf hash + Poseidon two-to-one, identity converter
+ * (R/merkle_tree/mod.rs:411-523).  leaf_nodes[n], non_leaf_nodes[n-1] in heap order. */
+int oref_poseidon_merkle(const poseidon_t *leafP, const poseidon_t *nodeP, const u64 *leaves, size_t leaf_len,
+                         size_t n, u64 *leaf_nodes, u64 *non_leaf_nodes, int threads) {
+    if (n < 2 || (n & (n - 1))) return 1;                                     /* :430-433 */
+    oref_poseidon_crh_batch(leafP, leaves, leaf_len, leaf_nodes, n, threads);   /* :417-419 */
+    fe *nodes = (fe *)non_leaf_nodes;
+    size_t start = n / 2 - 1;
+    oref_poseidon_compress_batch(nodeP, leaf_nodes, (u64 *)(nodes + start), n / 2, threads);   /* :454-483 */
+    while (start > 0) {                                                       /* :486-515 */
+        size_t upper = start;
+        start = (start - 1) / 2;
+        oref_poseidon_compress_batch(nodeP, (const u64 *)(nodes + upper), (u64 *)(nodes + start),
+                                     upper - start, threads);
+    }
+    return 0;
+}
+
+/* ---------------------------------------------------------------- twisted Edwards + Pedersen */
+
+typedef struct { fe x, y, t, z; } te_point;   /* extended coordinates, x=X/Z, y=Y/Z, t=XY/Z */
+
+typedef struct {
+    field_t F;
+    fe a, d;                  /* curve a*x^2 + y^2 = 1 + d*x^2*y^2 */
+    int window_size, num_windows;
+    size_t n_gens;            /* window_size*num_windows */
+    fe *gx, *gy;              /* generators[w][j] flattened, affine */
+    size_t n_rand;            /* randomness generators (0 for plain CRH) */
+    fe *rx, *ry;
+} pedersen_t;
+
+pedersen_t *oref_pedersen_new(const u64 p[4], const u64 *a_mont, const u64 *d_mont, int window_size,
+                              int num_windows, const u64 *gens_xy_mont, size_t n_rand, const u64 *rand_xy_mont) {
+    pedersen_t *P = (pedersen_t *)calloc(1, sizeof *P);
+    oref_field_init(&P->F, p);
+    memcpy(P->a.l, a_mont, 32);
+    memcpy(P->d.l, d_mont, 32);
+    P->window_size = window_size; P->num_windows = num_windows;
+    P->n_gens = (size_t)window_size * num_windows;
+    P->gx = (fe *)malloc(P->n_gens * sizeof(fe)); P->gy = (fe *)malloc(P->n_gens * sizeof(fe));
+    for (size_t i = 0; i < P->n_gens; i++) {
+        memcpy(P->gx[i].l, gens_xy_mont + 8 * i, 32);
+        memcpy(P->gy[i].l, gens_xy_mont + 8 * i + 4, 32);
+    }
+    P->n_rand = n_rand;
+    if (n_rand) {
+        P->rx = (fe *)malloc(n_rand * sizeof(fe)); P->ry = (fe *)malloc(n_rand * sizeof(fe));
+        for (size_t i = 0; i < n_rand; i++) {
+            memcpy(P->rx[i].l, rand_xy_mont + 8 * i, 32);
+            memcpy(P->ry[i].l, rand_xy_mont + 8 * i + 4, 32);
+        }
+    }
+    return P;
+}
+
+void oref_pedersen_free(pedersen_t *P) {
+    if (!P) return;
+    free(P->gx); free(P->gy); free(P->rx); free(P->ry); free(P);
+}
+
+/* Unified twisted-Edwards addition for general a (Hisil-Wong-Carter-Dawson, "add-2008-hwcd"):
+ * complete when a is a square and d a non-square.  acc += (x2,y2) affine. */
+static void te_add_affine(const pedersen_t *P, te_point *acc, const fe *x2, const fe *y2) {
+    const field_t *F = &P->F;
+    fe A, B, C, D, E, Fv, G, H, t2, tmp, tmp2;
+    fe_mul(F, &A, &acc->x, x2);
+    fe_mul(F, &B, &acc->y, y2);
+    fe_mul(F, &t2, x2, y2);
+    fe_mul(F, &C, &acc->t, &t2);
+    fe_mul(F, &C, &C, &P->d);
+    D = acc->z;
+    fe_add(F, &tmp, &acc->x, &acc->y);
+    fe_add(F, &tmp2, x2, y2);
+    fe_mul(F, &E, &tmp, &tmp2);
+    fe_sub(F, &E, &E, &A);
+    fe_sub(F, &E, &E, &B);
+    fe_sub(F, &Fv, &D, &C);
+    fe_add(F, &G, &D, &C);
+    fe_mul(F, &tmp, &P->a, &A);
+    fe_sub(F, &H, &B, &tmp);
+    fe_mul(F, &acc->x, &E, &Fv);
+    fe_mul(F, &acc->y, &G, &H);
+    fe_mul(F, &acc->t, &E, &H);
+    fe_mul(F, &acc->z, &Fv, &G);
+}
+
+static void te_identity(const pedersen_t *P, te_point *r) {
+    memset(r, 0, sizeof *r);
+    r->y = P->F.one;
+    r->z = P->F.one;
+}
+
+static void te_to_affine(const pedersen_t *P, const te_point *a, fe *x, fe *y) {
+    fe zi;
+    fe_inv(&P->F, &zi, &a->z);
+    fe_mul(&P->F, x, &a->x, &zi);
+    fe_mul(&P->F, y, &a->y, &zi);
+}
+
+/* pedersen::CRH::evaluate (R/crh/pedersen/mod.rs:76-129) on an already padded input of `len`
+ * bytes; optionally followed by the commitment's randomness sum
+ * (R/commitment/pedersen/mod.rs:93-100).  Returns 0, or 1 for "incorrect input length". */
+static int pedersen_one(const pedersen_t *P, const uint8_t *in, size_t len, const uint8_t *rand32, fe *ox, fe *oy) {
+    size_t nbits = P->n_gens;
+    if (len * 8 > nbits) return 1;                                  /* :82-89 (panic) */
+    size_t padded = len;
+    if (len * 8 < nbits) padded = nbits / 8 > len ? nbits / 8 : len;   /* :94-99 */
+    te_point acc;
+    te_identity(P, &acc);
+    size_t total_bits = padded * 8;
+    for (size_t w = 0; w < (size_t)P->num_windows; w++) {           /* chunks(WINDOW_SIZE).zip(generators) :113-124 */
+        for (size_t j = 0; j < (size_t)P->window_size; j++) {
+            size_t k = w * P->window_size + j;
+            if (k >= total_bits) break;
+            size_t byte = k >> 3;
+            int bit = byte < len ? (in[byte] >> (k & 7)) & 1 : 0;   /* bytes_to_bits :200-209 */
+            if (bit) te_add_affine(P, &acc, &P->gx[k], &P->gy[k]);
+        }
+    }
+    if (rand32) {
+        for (size_t k = 0; k < P->n_rand && k < 256; k++)
+            if ((rand32[k >> 3] >> (k & 7)) & 1) te_add_affine(P, &acc, &P->rx[k], &P->ry[k]);
+    }
+    te_to_affine(P, &acc, ox, oy);                                  /* :128 into() */
+    return 0;
+}
+
+typedef struct {
+    const pedersen_t *P; const uint8_t *in; size_t len, stride; const uint8_t *rand; u64 *out; int err;
+} ped_job;
+static void ped_range(void *c, size_t b, size_t e) {
+    ped_job *j = (ped_job *)c;
+    for (size_t i = b; i < e; i++) {
+        fe x, y;
+        if (pedersen_one(j->P, j->in + i * j->stride, j->len, j->rand ? j->rand + 32 * i : NULL, &x, &y)) {
+            j->err = 1;
+            return;
+        }
+        memcpy(j->out + 8 * i, x.l, 32);
+        memcpy(j->out + 8 * i + 4, y.l, 32);
+    }
+}
+
+/* n hashes of `len` bytes each (`stride` apart); out = n x (x,y) Montgomery. rand32: n x 32-byte
+ * little-endian canonical scalars for commit, or NULL for the CRH. */
+int oref_pedersen_batch(const pedersen_t *P, const uint8_t *in, size_t len, size_t stride, const uint8_t *rand32,
+                        u64 *out_xy, size_t n, int threads) {
+    ped_job j = {P, in, len, stride, rand32, out_xy, 0};
+    parallel_for(n, threads, ped_range, &j);
+    return j.err;
+}
+
+/* serialize_uncompressed of an affine TE point: canonical x || y, 32-byte LE each (dep). */
+static void point_bytes(const field_t *F, const u64 *xy_mont, uint8_t out[64]) {
+    u64 plain[8];
+    oref_from_mont(F, plain, xy_mont, 2);
+    memcpy(out, plain, 64);       /* little-endian host */
+}
+
+typedef struct { const pedersen_t *P; const u64 *children; u64 *out; int err; } pnode_job;
+static void pnode_range(void *c, size_t b, size_t e) {
+    pnode_job *j = (pnode_job *)c;
+    size_t half_bytes = j->P->n_gens / 2 / 8;
+    size_t buf_len = 2 * half_bytes;
+    uint8_t *buf = (uint8_t *)malloc(buf_len + 128);
+    for (size_t i = b; i < e; i++) {
+        uint8_t lr[128];
+        point_bytes(&j->P->F, j->children + 16 * i, lr);
+        point_bytes(&j->P->F, j->children + 16 * i + 8, lr + 64);
+        memset(buf, 0, buf_len);                                       /* R/crh/pedersen/mod.rs:173-180 */
+        memcpy(buf, lr, buf_len < 128 ? buf_len : 128);
+        fe x, y;
+        if (pedersen_one(j->P, buf, buf_len, NULL, &x, &y)) { j->err = 1; break; }
+        memcpy(j->out + 8 * i, x.l, 32);
+        memcpy(j->out + 8 * i + 4, y.l, 32);
+    }
+    free(buf);
+}
+
+/* TwoToOneCRH::compress over n (left,right) affine point pairs (R/crh/pedersen/mod.rs:187-197). */
+int oref_pedersen_compress_batch(const pedersen_t *P, const u64 *children_xy, u64 *out_xy, size_t n, int threads) {
+    pnode_job j = {P, children_xy, out_xy, 0};
+    parallel_for(n, threads, pnode_range, &j);
+    return j.err;
+}
+
+/* Byte-leaf Pedersen tree: LeafHash = pedersen::CRH, ByteDigestConverter, TwoToOneHash =
+ * pedersen::TwoToOneCRH (R/merkle_tree/tests/mod.rs:19-33).  Digests are (x,y) Montgomery. */
+int oref_pedersen_merkle(const pedersen_t *leafP, const pedersen_t *nodeP, const uint8_t *leaves, size_t leaf_len,
+                         size_t n, u64 *leaf_nodes_xy, u64 *non_leaf_nodes_xy, int threads) {
+    if (n < 2 || (n & (n - 1))) return 1;
+    if (oref_pedersen_batch(leafP, leaves, leaf_len, leaf_len, NULL, leaf_nodes_xy, n, threads)) return 2;
+    size_t start = n / 2 - 1;
+    if (oref_pedersen_compress_batch(nodeP, leaf_nodes_xy, non_leaf_nodes_xy + 8 * start, n / 2, threads)) return 2;
+    while (start > 0) {
+        size_t upper = start;
+        start = (start - 1) / 2;
+        if (oref_pedersen_compress_batch(nodeP, non_leaf_nodes_xy + 8 * upper, non_leaf_nodes_xy + 8 * start,
+                                         upper - start, threads)) return 2;
+    }
+    return 0;
+}
+
+/* Mixed tree (BASELINE config 5): LeafHash = PedersenCRHCompressor<_, TECompressor, W>
+ * (x-coordinate, R/crh/injective_map/mod.rs:22-62), identity converter, Poseidon two-to-one. */
+int oref_mixed_merkle(const pedersen_t *leafP, const poseidon_t *nodeP, const uint8_t *leaves, size_t leaf_len,
+                      size_t n, u64 *leaf_nodes, u64 *non_leaf_nodes, int threads) {
+    if (n < 2 || (n & (n - 1))) return 1;
+    u64 *xy = (u64 *)malloc(n * 64);
+    if (oref_pedersen_batch(leafP, leaves, leaf_len, leaf_len, NULL, xy, n, threads)) { free(xy); return 2; }
+    for (size_t i = 0; i < n; i++) memcpy(leaf_nodes + 4 * i, xy + 8 * i, 32);
+    free(xy);
+    fe *nodes = (fe *)non_leaf_nodes;
+    size_t start = n / 2 - 1;
+    oref_poseidon_compress_batch(nodeP, leaf_nodes, (u64 *)(nodes + start), n / 2, threads);
+    while (start > 0) {
+        size_t upper = start;
+        start = (start - 1) / 2;
+        oref_poseidon_compress_batch(nodeP, (const u64 *)(nodes + upper), (u64 *)(nodes + start), upper - start, threads);
+    }
+    return 0;
+}
