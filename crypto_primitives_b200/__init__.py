@@ -1,0 +1,16 @@
+"""crypto_primitives_b200 -- B200-native (sm_100a CUDA) batched evaluation of the
+ark-crypto-primitives hot path: Poseidon CRH / two-to-one, Pedersen CRH / commitment, and the
+Merkle-tree build over them, behind the reference's CRHScheme / TwoToOneCRHScheme /
+CommitmentScheme / merkle_tree::Config surface.  All hashing happens in libcpb200.so
+(csrc/, C-ABI in include/cpb200.h); this package is the host-side mirror of the reference's
+interface plus ctypes plumbing.  There is no CPU fallback: importing fails without the library,
+and every compute call fails without a B200.
+"""
+from . import _native
+from .fields import BLS12_381_FR, BLS12_377_FR, BN254_FR, JUBJUB_FR, FIELDS, Field
+from .sponge.poseidon import PoseidonConfig, find_poseidon_ark_and_mds, get_default_poseidon_parameters
+from .crh import poseidon as crh_poseidon
+from . import merkle_tree
+
+__all__ = ["Field", "FIELDS", "BLS12_381_FR", "BN254_FR", "JUBJUB_FR", "BLS12_377_FR", "PoseidonConfig",
+           "find_poseidon_ark_and_mds", "get_default_poseidon_parameters", "crh_poseidon", "merkle_tree"]

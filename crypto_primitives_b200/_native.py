@@ -1,0 +1,69 @@
+"""ctypes binding of libcpb200.so (include/cpb200.h).  Plumbing only: every computation happens in
+the CUDA library.  Importing this module never touches the GPU; the first context creation does.
+The library is loaded eagerly and its absence is an error -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcpb200.so")
+
+u64p = C.POINTER(C.c_uint64)
+u8p = C.POINTER(C.c_uint8)
+vp = C.c_void_p
+
+CPB_OK, CPB_BAD_LENGTH, CPB_BAD_PARAMS, CPB_NOT_POW2, CPB_CUDA_ERROR, CPB_NO_DEVICE, CPB_UNSUPPORTED, CPB_NULL_POINTER = range(8)
+
+# name -> (restype, argtypes); mirrors include/cpb200.h one to one (tests/test_abi.py checks it).
+SIGNATURES = {
+    "cpb_last_error": (C.c_char_p, []),
+    "cpb_version": (C.c_int, []),
+    "cpb_device_count": (C.c_int, []),
+    "cpb_field_modulus": (C.c_int, [C.c_int, u64p]),
+    "cpb_field_to_montgomery": (C.c_int, [C.c_int, C.c_int, u64p, u64p, C.c_size_t]),
+    "cpb_field_from_montgomery": (C.c_int, [C.c_int, C.c_int, u64p, u64p, C.c_size_t]),
+    "cpb_poseidon_find_ark_and_mds": (C.c_int, [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, u64p, u64p]),
+    "cpb_poseidon_default_entry": (C.c_int, [C.c_int, C.c_int, u64p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cpb_poseidon_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, u64p, u64p, C.c_int, C.POINTER(vp)]),
+    "cpb_poseidon_ctx_destroy": (None, [vp]),
+    "cpb_poseidon_ctx_is_sparse": (C.c_int, [vp]),
+    "cpb_poseidon_permute_batch": (C.c_int, [vp, u64p, u64p, C.c_size_t]),
+    "cpb_poseidon_permute_batch_dev": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
+    "cpb_poseidon_crh_batch": (C.c_int, [vp, u64p, C.c_size_t, u64p, C.c_size_t]),
+    "cpb_poseidon_crh_batch_dev": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t, vp]),
+    "cpb_poseidon_compress_batch": (C.c_int, [vp, u64p, u64p, C.c_size_t]),
+    "cpb_poseidon_compress_batch_dev": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
+    "cpb_merkle_poseidon_build": (C.c_int, [vp, vp, u64p, C.c_size_t, C.c_size_t, u64p, u64p]),
+    "cpb_merkle_poseidon_build_dev": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_size_t, vp, vp, vp]),
+    "cpb_merkle_poseidon_from_digests": (C.c_int, [vp, u64p, C.c_size_t, u64p]),
+    "cpb_merkle_poseidon_from_digests_dev": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
+}
+
+
+class CpbError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"cpb status {status}: {message}")
+        self.status = status
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m crypto_primitives_b200._build` "
+            "(nvcc, sm_100a).  crypto_primitives_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError if the library does not export the symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(status: int):
+    if status != CPB_OK:
+        raise CpbError(status, lib.cpb_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,478 @@
+// cpb_poseidon.cu -- CUDA kernels + C-ABI for the Poseidon part of the hot path and the
+// field-leaf Merkle build on top of it (include/cpb200.h).
+//
+// Kernels (sm_100a, integer pipe, no tensor cores):
+//   k_poseidon_crh      one CRH::evaluate per thread (R/crh/poseidon/mod.rs:30-40); with len==2
+//                       it is also TwoToOneCRH::compress (:66-79) and one Merkle level
+//                       (R/merkle_tree/mod.rs:454-515), because a level's children are contiguous
+//                       in the heap-ordered node array.
+//   k_poseidon_permute  one bare permutation per thread (R/sponge/poseidon/mod.rs:98-121).
+//   k_field_convert     canonical <-> Montgomery.
+// Round constants / MDS / sparse rows are staged into shared memory with one TMA bulk copy per
+// CTA; inputs are read with 128-bit loads; state lives in registers.
+#include <vector>
+
+#include "common.cuh"
+#include "poseidon.cuh"
+#include "poseidon_host.hpp"
+
+namespace cpb {
+
+// ------------------------------------------------------------------------------ common impl
+std::string& last_error_ref() {
+    static thread_local std::string s;
+    return s;
+}
+cpb_status fail(cpb_status st, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return st;
+}
+int sm_count(int device) {
+    static int cache[64];
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    if (device < 0 || device >= 64) return 148;
+    if (!cache[device]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+        cache[device] = v;
+    }
+    return cache[device];
+}
+
+// ------------------------------------------------------------------------------ kernels
+constexpr int kBlock = 128;
+
+template <class F, int T>
+__global__ void __launch_bounds__(kBlock)
+k_poseidon_crh(PoseidonDev P, const u32* __restrict__ consts, const u32* __restrict__ in, u32* __restrict__ out,
+               long n, long len) {
+    extern __shared__ __align__(16) u32 cs[];
+    __shared__ __align__(8) unsigned long long mbar;
+    tma_stage_to_smem(cs, consts, (unsigned)P.n_elems * 32u, &mbar);
+    const u32* ct = cs + (int)threadIdx.x * P.zero;   // == cs, but not provably warp-uniform
+    u32 pm[8];
+    ld_elem(pm, ct + 8 * P.off_mod);
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        u32 r[8];
+        pos_crh<F, T>(r, in + 8 * len * i, len, P, ct, pm);
+        st_elem(out + 8 * i, r);
+    }
+}
+
+template <class F, int T>
+__global__ void __launch_bounds__(kBlock)
+k_poseidon_permute(PoseidonDev P, const u32* __restrict__ consts, const u32* __restrict__ in, u32* __restrict__ out,
+                   long n) {
+    extern __shared__ __align__(16) u32 cs[];
+    __shared__ __align__(8) unsigned long long mbar;
+    tma_stage_to_smem(cs, consts, (unsigned)P.n_elems * 32u, &mbar);
+    const u32* ct = cs + (int)threadIdx.x * P.zero;
+    u32 pm[8];
+    ld_elem(pm, ct + 8 * P.off_mod);
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        u32 s[T][8];
+#pragma unroll
+        for (int j = 0; j < T; j++) ld_elem(s[j], in + 8 * (T * i + j));
+        pos_permute<F, T>(s, P, ct, pm);
+#pragma unroll
+        for (int j = 0; j < T; j++) st_elem(out + 8 * (T * i + j), s[j]);
+    }
+}
+
+template <class F>
+__global__ void k_field_convert(const u32* __restrict__ in, u32* __restrict__ out, long n, int to_mont) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 a[8], k[8];
+    ld_elem(a, in + 8 * i);
+    if (to_mont) {
+        // inputs < 2^256 may exceed p: subtract p while >= p (at most 6 times for a 252-bit p... bounded loop)
+        for (int it = 0; it < 18; it++) {
+            u32 t[8];
+            t[0] = sub_cc(a[0], F::P(0));
+#pragma unroll
+            for (int j = 1; j < 8; j++) t[j] = subc_cc(a[j], F::P(j));
+            u32 borrow = subc(0, 0);
+            if (borrow) break;
+            fp_copy(a, t);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) k[j] = F::R2(j);
+    } else {
+        fp_zero(k);
+        k[0] = 1;
+    }
+    u32 pm[8];
+    fp_modulus<F>(pm);
+    fp_mul<F>(a, a, k, pm);
+    st_elem(out + 8 * i, a);
+}
+
+}  // namespace cpb
+
+using namespace cpb;
+
+// ------------------------------------------------------------------------------ context
+struct cpb_poseidon_ctx {
+    int field_id = 0, device = 0, sms = 148;
+    host::PoseidonSchedule sched;
+    PoseidonDev dev{};
+    u32* d_consts = nullptr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    Scratch s_in, s_out, s_aux;
+};
+
+namespace {
+
+PoseidonDev to_dev(const host::PoseidonSchedule& S) {
+    PoseidonDev D;
+    D.t = S.t; D.rate = S.rate; D.cap = S.capacity; D.rf = S.rf; D.rp = S.rp; D.sparse = S.sparse; D.alpha = S.alpha;
+    D.off_c = S.off_c; D.off_m = S.off_m; D.off_mpre = S.off_mpre; D.off_cp0 = S.off_cp0; D.off_pc = S.off_pc;
+    D.off_sp = S.off_sp; D.off_arkp = S.off_arkp; D.off_mod = S.off_mod; D.n_elems = S.n_elems; D.zero = 0;
+    return D;
+}
+
+template <class K> cpb_status grid_for(K kernel, size_t smem, int sms, long n, int& grid) {
+    static thread_local const void* last = nullptr;
+    static thread_local int last_occ = 0;
+    static thread_local size_t last_smem = 0;
+    if (last != (const void*)kernel || last_smem != smem) {
+        if (smem > 48 * 1024) CPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, smem));
+        if (occ < 1) return fail(CPB_CUDA_ERROR, "kernel does not fit on an SM (smem=%zu)", smem);
+        last = (const void*)kernel; last_occ = occ; last_smem = smem;
+    }
+    long need = (n + kBlock - 1) / kBlock;
+    long cap = (long)sms * last_occ;     // persistent: one wave, grid-stride inside
+    grid = (int)(need < cap ? need : cap);
+    if (grid < 1) grid = 1;
+    return CPB_OK;
+}
+
+template <class F, int T>
+cpb_status launch_crh_ft(cpb_poseidon_ctx* c, const u32* in, size_t len, u32* out, size_t n, cudaStream_t st) {
+    size_t smem = (size_t)c->dev.n_elems * 32;
+    int grid = 1;
+    CPB_TRY(grid_for(k_poseidon_crh<F, T>, smem, c->sms, (long)n, grid));
+    k_poseidon_crh<F, T><<<grid, kBlock, smem, st>>>(c->dev, c->d_consts, in, out, (long)n, (long)len);
+    CPB_CUDA(cudaGetLastError());
+    return CPB_OK;
+}
+template <class F, int T>
+cpb_status launch_permute_ft(cpb_poseidon_ctx* c, const u32* in, u32* out, size_t n, cudaStream_t st) {
+    size_t smem = (size_t)c->dev.n_elems * 32;
+    int grid = 1;
+    CPB_TRY(grid_for(k_poseidon_permute<F, T>, smem, c->sms, (long)n, grid));
+    k_poseidon_permute<F, T><<<grid, kBlock, smem, st>>>(c->dev, c->d_consts, in, out, (long)n);
+    CPB_CUDA(cudaGetLastError());
+    return CPB_OK;
+}
+
+#define CPB_FOR_FIELD(fid, M, ...)                                                      \
+    switch (fid) {                                                                      \
+        case CPB_BLS12_381_FR: return M<Bls12_381_Fr, 3>(__VA_ARGS__);                  \
+        case CPB_BN254_FR: return M<Bn254_Fr, 3>(__VA_ARGS__);                          \
+        case CPB_JUBJUB_FR: return M<Jubjub_Fr, 3>(__VA_ARGS__);                        \
+        case CPB_BLS12_377_FR: return M<Bls12_377_Fr, 3>(__VA_ARGS__);                  \
+    }
+
+cpb_status launch_crh(cpb_poseidon_ctx* c, const u32* in, size_t len, u32* out, size_t n, cudaStream_t st) {
+    if (n == 0) return CPB_OK;
+    if (c->dev.t == 3) { CPB_FOR_FIELD(c->field_id, launch_crh_ft, c, in, len, out, n, st) }
+    return fail(CPB_UNSUPPORTED, "state width t=%d not built (this build: t=3)", c->dev.t);
+}
+cpb_status launch_permute(cpb_poseidon_ctx* c, const u32* in, u32* out, size_t n, cudaStream_t st) {
+    if (n == 0) return CPB_OK;
+    if (c->dev.t == 3) { CPB_FOR_FIELD(c->field_id, launch_permute_ft, c, in, out, n, st) }
+    return fail(CPB_UNSUPPORTED, "state width t=%d not built (this build: t=3)", c->dev.t);
+}
+
+cpb_status check_ctx(const cpb_poseidon_ctx* c) {
+    if (!c) return fail(CPB_NULL_POINTER, "null context");
+    return CPB_OK;
+}
+
+// heap-ordered inner levels from n leaf digests (new_with_leaf_digest, R/merkle_tree/mod.rs:424-523)
+cpb_status merkle_levels(cpb_poseidon_ctx* node, const u32* leaf_digests, size_t n, u32* nodes, cudaStream_t st) {
+    size_t start = n / 2 - 1;
+    CPB_TRY(launch_crh(node, leaf_digests, 2, nodes + 8 * start, n / 2, st));
+    while (start > 0) {
+        size_t upper = start;
+        start = (start - 1) / 2;
+        CPB_TRY(launch_crh(node, nodes + 8 * upper, 2, nodes + 8 * start, upper - start, st));
+    }
+    return CPB_OK;
+}
+
+bool pow2_gt1(size_t n) { return n > 1 && (n & (n - 1)) == 0; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* cpb_last_error(void) { return last_error_ref().c_str(); }
+int cpb_version(void) { return 100; }
+
+int cpb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; d++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+cpb_status cpb_field_modulus(int field_id, uint64_t out[4]) {
+    const uint64_t* m = host::field_modulus(field_id);
+    if (!m) return fail(CPB_BAD_PARAMS, "unknown field id %d", field_id);
+    if (!out) return fail(CPB_NULL_POINTER, "null out");
+    memcpy(out, m, 32);
+    return CPB_OK;
+}
+
+static cpb_status field_convert(int field_id, int device, const uint64_t* in, uint64_t* out, size_t n, int to_mont) {
+    if (!host::field_modulus(field_id)) return fail(CPB_BAD_PARAMS, "unknown field id %d", field_id);
+    if (n == 0) return CPB_OK;
+    if (!in || !out) return fail(CPB_NULL_POINTER, "null buffer");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(CPB_NO_DEVICE, "cudaSetDevice(%d) failed", device);
+    u32* d = nullptr;
+    CPB_CUDA(cudaMalloc(&d, n * 32));
+    cudaError_t e = cudaMemcpy(d, in, n * 32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        int grid = (int)((n + 127) / 128);
+        switch (field_id) {
+            case 0: k_field_convert<Bls12_381_Fr><<<grid, 128>>>(d, d, (long)n, to_mont); break;
+            case 1: k_field_convert<Bn254_Fr><<<grid, 128>>>(d, d, (long)n, to_mont); break;
+            case 2: k_field_convert<Jubjub_Fr><<<grid, 128>>>(d, d, (long)n, to_mont); break;
+            case 3: k_field_convert<Bls12_377_Fr><<<grid, 128>>>(d, d, (long)n, to_mont); break;
+        }
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d, n * 32, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(CPB_CUDA_ERROR, "field conversion failed: %s", cudaGetErrorString(e));
+    return CPB_OK;
+}
+cpb_status cpb_field_to_montgomery(int field_id, int device, const uint64_t* in, uint64_t* out, size_t n) {
+    return field_convert(field_id, device, in, out, n, 1);
+}
+cpb_status cpb_field_from_montgomery(int field_id, int device, const uint64_t* in, uint64_t* out, size_t n) {
+    return field_convert(field_id, device, in, out, n, 0);
+}
+
+cpb_status cpb_poseidon_find_ark_and_mds(int field_id, uint64_t prime_bits, int rate, int full_rounds,
+                                         int partial_rounds, int skip_matrices, uint64_t* ark_out, uint64_t* mds_out) {
+    const uint64_t* mod = host::field_modulus(field_id);
+    if (!mod) return fail(CPB_BAD_PARAMS, "unknown field id %d", field_id);
+    if (!ark_out || !mds_out) return fail(CPB_NULL_POINTER, "null output");
+    host::Field F(mod);
+    if (prime_bits != (uint64_t)F.bits)   // assert_eq!(F::MODULUS_BIT_SIZE, prime_num_bits), grain_lfsr.rs:113
+        return fail(CPB_BAD_PARAMS, "prime_bits %llu != MODULUS_BIT_SIZE %d", (unsigned long long)prime_bits, F.bits);
+    if (rate < 1 || rate > 15 || full_rounds < 0 || partial_rounds < 0 || full_rounds > 1023 || partial_rounds > 1023 ||
+        skip_matrices < 0)
+        return fail(CPB_BAD_PARAMS, "bad shape");
+    host::FeVec ark, mds;
+    host::find_poseidon_ark_and_mds(F, prime_bits, rate, full_rounds, partial_rounds, skip_matrices, ark, mds);
+    memcpy(ark_out, ark.data(), ark.size() * 32);
+    memcpy(mds_out, mds.data(), mds.size() * 32);
+    return CPB_OK;
+}
+
+cpb_status cpb_poseidon_default_entry(int rate, int optimized_for_weights, uint64_t* alpha, int* full_rounds,
+                                      int* partial_rounds, int* skip_matrices) {
+    host::DefaultEntry e;
+    if (!host::default_entry(rate, optimized_for_weights != 0, e))
+        return fail(CPB_BAD_PARAMS, "no default entry for rate %d", rate);   // reference returns None
+    if (alpha) *alpha = e.alpha;
+    if (full_rounds) *full_rounds = e.rf;
+    if (partial_rounds) *partial_rounds = e.rp;
+    if (skip_matrices) *skip_matrices = e.skip;
+    return CPB_OK;
+}
+
+cpb_status cpb_poseidon_ctx_create(int field_id, int rate, int capacity, int full_rounds, int partial_rounds,
+                                   uint64_t alpha, const uint64_t* ark, const uint64_t* mds, int device,
+                                   cpb_poseidon_ctx** out) {
+    if (!out) return fail(CPB_NULL_POINTER, "null out");
+    *out = nullptr;
+    const uint64_t* mod = host::field_modulus(field_id);
+    if (!mod) return fail(CPB_BAD_PARAMS, "unknown field id %d", field_id);
+    if (!ark || !mds) return fail(CPB_NULL_POINTER, "null ark/mds");
+    if (rate < 1 || capacity < 1 || rate + capacity > 16 || full_rounds < 0 || partial_rounds < 0 ||
+        full_rounds + partial_rounds < 1 || (full_rounds & 1))
+        return fail(CPB_BAD_PARAMS, "bad Poseidon shape rate=%d capacity=%d RF=%d RP=%d", rate, capacity, full_rounds,
+                    partial_rounds);
+    host::Field F(mod);
+    host::PoseidonParams P;
+    P.rate = rate; P.capacity = capacity; P.full_rounds = full_rounds; P.partial_rounds = partial_rounds; P.alpha = alpha;
+    int t = rate + capacity;
+    P.ark.resize((size_t)(full_rounds + partial_rounds) * t);
+    P.mds.resize((size_t)t * t);
+    memcpy(P.ark.data(), ark, P.ark.size() * 32);
+    memcpy(P.mds.data(), mds, P.mds.size() * 32);
+    for (const auto& e : P.ark)
+        if (!F.is_canonical(e)) return fail(CPB_BAD_PARAMS, "ark element not reduced");
+    for (const auto& e : P.mds)
+        if (!F.is_canonical(e)) return fail(CPB_BAD_PARAMS, "mds element not reduced");
+
+    DeviceGuard g(device);
+    if (!g.ok) { cudaGetLastError(); return fail(CPB_NO_DEVICE, "cudaSetDevice(%d) failed: no usable CUDA device", device); }
+    int major = 0;
+    CPB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return fail(CPB_NO_DEVICE, "device %d is sm_%d0; this library is built for sm_100a only", device, major);
+
+    cpb_poseidon_ctx* c = new cpb_poseidon_ctx();
+    c->field_id = field_id;
+    c->device = device;
+    c->sms = sm_count(device);
+    c->sched = host::derive_schedule(F, P, true);
+    c->dev = to_dev(c->sched);
+    size_t bytes = c->sched.consts.size() * 8;
+    if (bytes > 200 * 1024) { delete c; return fail(CPB_UNSUPPORTED, "round schedule (%zu B) exceeds shared memory", bytes); }
+    cudaError_t e = cudaMalloc(&c->d_consts, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_consts, c->sched.consts.data(), bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        if (c->d_consts) cudaFree(c->d_consts);
+        delete c;
+        return fail(CPB_CUDA_ERROR, "context upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return CPB_OK;
+}
+
+void cpb_poseidon_ctx_destroy(cpb_poseidon_ctx* c) {
+    if (!c) return;
+    DeviceGuard g(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->d_consts) cudaFree(c->d_consts);
+    c->s_in.release(); c->s_out.release(); c->s_aux.release();
+    delete c;
+}
+
+int cpb_poseidon_ctx_is_sparse(const cpb_poseidon_ctx* c) { return c ? c->sched.sparse : 0; }
+
+// ---- device-pointer entry points
+cpb_status cpb_poseidon_permute_batch_dev(cpb_poseidon_ctx* c, const uint64_t* in, uint64_t* out, size_t n, void* stream) {
+    CPB_TRY(check_ctx(c));
+    DeviceGuard g(c->device);
+    return launch_permute(c, (const u32*)in, (u32*)out, n, (cudaStream_t)stream);
+}
+cpb_status cpb_poseidon_crh_batch_dev(cpb_poseidon_ctx* c, const uint64_t* in, size_t len, uint64_t* out, size_t n, void* stream) {
+    CPB_TRY(check_ctx(c));
+    DeviceGuard g(c->device);
+    return launch_crh(c, (const u32*)in, len, (u32*)out, n, (cudaStream_t)stream);
+}
+cpb_status cpb_poseidon_compress_batch_dev(cpb_poseidon_ctx* c, const uint64_t* pairs, uint64_t* out, size_t n, void* stream) {
+    CPB_TRY(check_ctx(c));
+    if (c->dev.rate < 2)   // two absorbs then one squeeze = one permutation only when rate >= 2
+        return fail(CPB_UNSUPPORTED, "two-to-one with rate < 2 not supported");
+    DeviceGuard g(c->device);
+    return launch_crh(c, (const u32*)pairs, 2, (u32*)out, n, (cudaStream_t)stream);
+}
+cpb_status cpb_merkle_poseidon_from_digests_dev(cpb_poseidon_ctx* node, const uint64_t* leaf_digests, size_t n,
+                                                uint64_t* non_leaf_nodes, void* stream) {
+    CPB_TRY(check_ctx(node));
+    if (!pow2_gt1(n)) return fail(CPB_NOT_POW2, "leaves.len() should be power of two and greater than one (got %zu)", n);
+    if (node->dev.rate < 2) return fail(CPB_UNSUPPORTED, "two-to-one with rate < 2 not supported");
+    DeviceGuard g(node->device);
+    return merkle_levels(node, (const u32*)leaf_digests, n, (u32*)non_leaf_nodes, (cudaStream_t)stream);
+}
+cpb_status cpb_merkle_poseidon_build_dev(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, const uint64_t* leaves,
+                                         size_t leaf_len, size_t n, uint64_t* leaf_nodes, uint64_t* non_leaf_nodes,
+                                         void* stream) {
+    CPB_TRY(check_ctx(leaf));
+    CPB_TRY(check_ctx(node));
+    if (leaf->device != node->device || leaf->field_id != node->field_id)
+        return fail(CPB_BAD_PARAMS, "leaf and node contexts must share device and field");
+    if (!pow2_gt1(n)) return fail(CPB_NOT_POW2, "leaves.len() should be power of two and greater than one (got %zu)", n);
+    if (node->dev.rate < 2) return fail(CPB_UNSUPPORTED, "two-to-one with rate < 2 not supported");
+    DeviceGuard g(leaf->device);
+    CPB_TRY(launch_crh(leaf, (const u32*)leaves, leaf_len, (u32*)leaf_nodes, n, (cudaStream_t)stream));
+    return merkle_levels(node, (const u32*)leaf_nodes, n, (u32*)non_leaf_nodes, (cudaStream_t)stream);
+}
+
+// ---- host-pointer entry points: H2D, launch, D2H on the context stream
+static cpb_status host_roundtrip_crh(cpb_poseidon_ctx* c, const uint64_t* in, size_t in_elems_per, size_t len,
+                                     uint64_t* out, size_t out_elems_per, size_t n, int mode) {
+    CPB_TRY(check_ctx(c));
+    if (n == 0) return CPB_OK;
+    if ((!in && in_elems_per) || !out) return fail(CPB_NULL_POINTER, "null buffer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    size_t in_b = n * in_elems_per * 32, out_b = n * out_elems_per * 32;
+    CPB_TRY(c->s_in.reserve(in_b ? in_b : 32));
+    CPB_TRY(c->s_out.reserve(out_b));
+    if (in_b) CPB_CUDA(cudaMemcpyAsync(c->s_in.ptr, in, in_b, cudaMemcpyHostToDevice, c->stream));
+    if (mode == 0) CPB_TRY(launch_crh(c, (const u32*)c->s_in.ptr, len, (u32*)c->s_out.ptr, n, c->stream));
+    else CPB_TRY(launch_permute(c, (const u32*)c->s_in.ptr, (u32*)c->s_out.ptr, n, c->stream));
+    CPB_CUDA(cudaMemcpyAsync(out, c->s_out.ptr, out_b, cudaMemcpyDeviceToHost, c->stream));
+    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    return CPB_OK;
+}
+cpb_status cpb_poseidon_permute_batch(cpb_poseidon_ctx* c, const uint64_t* in, uint64_t* out, size_t n) {
+    CPB_TRY(check_ctx(c));
+    return host_roundtrip_crh(c, in, (size_t)c->dev.t, 0, out, (size_t)c->dev.t, n, 1);
+}
+cpb_status cpb_poseidon_crh_batch(cpb_poseidon_ctx* c, const uint64_t* in, size_t len, uint64_t* out, size_t n) {
+    return host_roundtrip_crh(c, in, len, len, out, 1, n, 0);
+}
+cpb_status cpb_poseidon_compress_batch(cpb_poseidon_ctx* c, const uint64_t* pairs, uint64_t* out, size_t n) {
+    CPB_TRY(check_ctx(c));
+    if (c->dev.rate < 2) return fail(CPB_UNSUPPORTED, "two-to-one with rate < 2 not supported");
+    return host_roundtrip_crh(c, pairs, 2, 2, out, 1, n, 0);
+}
+
+cpb_status cpb_merkle_poseidon_from_digests(cpb_poseidon_ctx* node, const uint64_t* leaf_digests, size_t n,
+                                            uint64_t* non_leaf_nodes) {
+    CPB_TRY(check_ctx(node));
+    if (!pow2_gt1(n)) return fail(CPB_NOT_POW2, "leaves.len() should be power of two and greater than one (got %zu)", n);
+    if (!leaf_digests || !non_leaf_nodes) return fail(CPB_NULL_POINTER, "null buffer");
+    std::lock_guard<std::mutex> lk(node->mu);
+    DeviceGuard g(node->device);
+    CPB_TRY(node->s_in.reserve(n * 32));
+    CPB_TRY(node->s_out.reserve((n - 1) * 32));
+    CPB_CUDA(cudaMemcpyAsync(node->s_in.ptr, leaf_digests, n * 32, cudaMemcpyHostToDevice, node->stream));
+    CPB_TRY(cpb_merkle_poseidon_from_digests_dev(node, (const uint64_t*)node->s_in.ptr, n, (uint64_t*)node->s_out.ptr, node->stream));
+    CPB_CUDA(cudaMemcpyAsync(non_leaf_nodes, node->s_out.ptr, (n - 1) * 32, cudaMemcpyDeviceToHost, node->stream));
+    CPB_CUDA(cudaStreamSynchronize(node->stream));
+    return CPB_OK;
+}
+
+cpb_status cpb_merkle_poseidon_build(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, const uint64_t* leaves,
+                                     size_t leaf_len, size_t n, uint64_t* leaf_nodes, uint64_t* non_leaf_nodes) {
+    CPB_TRY(check_ctx(leaf));
+    CPB_TRY(check_ctx(node));
+    if (!pow2_gt1(n)) return fail(CPB_NOT_POW2, "leaves.len() should be power of two and greater than one (got %zu)", n);
+    if ((!leaves && leaf_len) || !leaf_nodes || !non_leaf_nodes) return fail(CPB_NULL_POINTER, "null buffer");
+    std::lock_guard<std::mutex> lk(leaf->mu);
+    DeviceGuard g(leaf->device);
+    size_t in_b = n * leaf_len * 32;
+    CPB_TRY(leaf->s_in.reserve(in_b ? in_b : 32));
+    CPB_TRY(leaf->s_out.reserve(n * 32));
+    CPB_TRY(leaf->s_aux.reserve((n - 1) * 32));
+    cudaStream_t st = leaf->stream;
+    if (in_b) CPB_CUDA(cudaMemcpyAsync(leaf->s_in.ptr, leaves, in_b, cudaMemcpyHostToDevice, st));
+    CPB_TRY(cpb_merkle_poseidon_build_dev(leaf, node, (const uint64_t*)leaf->s_in.ptr, leaf_len, n,
+                                          (uint64_t*)leaf->s_out.ptr, (uint64_t*)leaf->s_aux.ptr, st));
+    CPB_CUDA(cudaMemcpyAsync(leaf_nodes, leaf->s_out.ptr, n * 32, cudaMemcpyDeviceToHost, st));
+    CPB_CUDA(cudaMemcpyAsync(non_leaf_nodes, leaf->s_aux.ptr, (n - 1) * 32, cudaMemcpyDeviceToHost, st));
+    CPB_CUDA(cudaStreamSynchronize(st));
+    return CPB_OK;
+}
+
+}  // extern "C"

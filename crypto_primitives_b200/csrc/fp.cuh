@@ -1,0 +1,362 @@
+// fp.cuh -- 256-bit prime-field arithmetic in Montgomery form (R = 2^256) on 8 x 32-bit
+// limbs held in registers; compile-time modulus per field tag.
+//
+// Replaces, for the device hot path, what the reference gets from ark-ff's
+// Fp<MontBackend<_,4>,4> (third-party; call sites R/sponge/poseidon/mod.rs:70,75,81,90-91,
+// R/crh/pedersen/mod.rs:116-124).  The memory image of an element is identical to ark-ff's:
+// 4 x u64 little-endian limbs == 8 x u32 little-endian limbs, Montgomery form, fully reduced.
+//
+// mont_mul is CIOS with the even/odd accumulator split: products a[j]*b_i for even j are
+// 64-bit values at even limb offsets and form one carry chain (one IMAD.WIDE.U32.X each);
+// odd j form a second chain one limb higher.  Dividing by 2^32 after each reduction row swaps
+// the roles of the two accumulators, so the shift costs no instructions.
+#pragma once
+#include "ptx.cuh"
+
+namespace cpb {
+
+// ---------------------------------------------------------------------------------------
+// Field tags.  limb(i) getters fold to immediates once loops are unrolled.
+// ---------------------------------------------------------------------------------------
+#define CPB_FIELD_TABLE(NAME, ...)                                   \
+    static CPB_HD constexpr u32 NAME(int i) {                        \
+        constexpr u32 v[8] = {__VA_ARGS__};                          \
+        return v[i];                                                 \
+    }
+
+struct Bls12_381_Fr {
+    static constexpr int ID = 0;
+    static constexpr u32 NINV = 0xffffffffu;
+    static constexpr int BITS = 255;
+    CPB_FIELD_TABLE(P, 0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u)
+    CPB_FIELD_TABLE(ONE, 0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau, 0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u)
+    CPB_FIELD_TABLE(R2, 0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u)
+};
+struct Bn254_Fr {
+    static constexpr int ID = 1;
+    static constexpr u32 NINV = 0xefffffffu;
+    static constexpr int BITS = 254;
+    CPB_FIELD_TABLE(P, 0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u)
+    CPB_FIELD_TABLE(ONE, 0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u)
+    CPB_FIELD_TABLE(R2, 0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u)
+};
+struct Jubjub_Fr {
+    static constexpr int ID = 2;
+    static constexpr u32 NINV = 0xef788ef9u;
+    static constexpr int BITS = 252;
+    CPB_FIELD_TABLE(P, 0xd6f72cb7u, 0xd0970e5eu, 0xccc81082u, 0xa6682093u, 0x01343b00u, 0x06673b01u, 0x6533afa9u, 0x0e7db4eau)
+    CPB_FIELD_TABLE(ONE, 0xb99607d9u, 0x25f80bb3u, 0x66b6e750u, 0xf315d62fu, 0xeb8814f4u, 0x932514eeu, 0x479155c6u, 0x09a6fc6fu)
+    CPB_FIELD_TABLE(R2, 0x95e57731u, 0x67719aa4u, 0x9ce3fc26u, 0x51b0cef0u, 0xc026e9a5u, 0x69dab7fau, 0x8d127688u, 0x04f6547bu)
+};
+struct Bls12_377_Fr {
+    static constexpr int ID = 3;
+    static constexpr u32 NINV = 0xffffffffu;
+    static constexpr int BITS = 253;
+    CPB_FIELD_TABLE(P, 0x00000001u, 0x0a118000u, 0xd0000001u, 0x59aa76feu, 0x5c37b001u, 0x60b44d1eu, 0x9a2ca556u, 0x12ab655eu)
+    CPB_FIELD_TABLE(ONE, 0xfffffff3u, 0x7d1c7fffu, 0x6ffffff2u, 0x7257f50fu, 0x512c0feeu, 0x16d81575u, 0x2bbb9a9du, 0x0d4bda32u)
+    CPB_FIELD_TABLE(R2, 0xb861857bu, 0x25d577bau, 0x8860591fu, 0xcc2c27b5u, 0xe5dc8593u, 0xa7cc008fu, 0xeff1c939u, 0x011fdae7u)
+};
+
+// ---------------------------------------------------------------------------------------
+// Element-wise helpers (all loops fully unrolled: limbs live in registers).
+// ---------------------------------------------------------------------------------------
+CPB_HD void fp_copy(u32* r, const u32* a) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = a[i];
+}
+CPB_HD void fp_zero(u32* r) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = 0;
+}
+template <class F> CPB_HD void fp_one(u32* r) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = F::ONE(i);
+}
+CPB_HD bool fp_eq(const u32* a, const u32* b) {
+    u32 d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d |= a[i] ^ b[i];
+    return d == 0;
+}
+
+// The multiplier takes the modulus limbs as a register array `pm` (loaded once per kernel from
+// shared memory): ptxas fuses mad.lo.cc/madc.hi.cc into one IMAD.WIDE.U32.X only when both
+// factors are ordinary registers -- with an immediate or constant-bank factor it emits
+// IMAD.X + IMAD.HI.U32.X, doubling the reduction cost (seen in cuobjdump -sass).  Additive
+// paths keep the modulus as immediates (F::P), which costs no registers.
+template <class F> CPB_HD void fp_modulus(u32* pm) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) pm[i] = F::P(i);
+}
+
+// r in [0, 2p) -> [0, p).  Requires 2p < 2^256 (true for every field tag above).
+template <class F> CPB_HD void fp_final_sub(u32* r) {
+    u32 t[8];
+    t[0] = sub_cc(r[0], F::P(0));
+#pragma unroll
+    for (int i = 1; i < 8; i++) t[i] = subc_cc(r[i], F::P(i));
+    u32 borrow = subc(0, 0);   // 0xffffffff when r < p
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = borrow ? r[i] : t[i];
+}
+
+template <class F> CPB_HD void fp_add(u32* r, const u32* a, const u32* b) {
+    r[0] = add_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r[i] = addc_cc(a[i], b[i]);
+    r[7] = addc(a[7], b[7]);   // a+b < 2p < 2^256
+    fp_final_sub<F>(r);
+}
+
+template <class F> CPB_HD void fp_sub(u32* r, const u32* a, const u32* b) {
+    u32 t[8];
+    t[0] = sub_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) t[i] = subc_cc(a[i], b[i]);
+    u32 borrow = subc(0, 0);
+    r[0] = add_cc(t[0], F::P(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r[i] = addc_cc(t[i], F::P(i) & borrow);
+    r[7] = addc(t[7], F::P(7) & borrow);
+}
+
+template <class F> CPB_HD void fp_double(u32* r, const u32* a) { fp_add<F>(r, a, a); }
+
+// ---------------------------------------------------------------------------------------
+// Montgomery multiplication.
+// ---------------------------------------------------------------------------------------
+namespace detail {
+
+// V += m*p with m chosen so the low limb of V = E + 2^32*O becomes zero.
+template <class F> CPB_HD void redc_row(u32* E, u32* O, const u32* pm) {
+    u32 m = (F::NINV == 0xffffffffu) ? (0u - E[0]) : mul_lo(E[0], F::NINV);
+    mad_wide_cc(O[0], O[1], pm[1], m);
+    madc_wide_cc(O[2], O[3], pm[3], m);
+    madc_wide_cc(O[4], O[5], pm[5], m);
+    madc_wide_cc(O[6], O[7], pm[7], m);   // no carry out: V < 2^288
+    mad_wide_cc(E[0], E[1], pm[0], m);
+    madc_wide_cc(E[2], E[3], pm[2], m);
+    madc_wide_cc(E[4], E[5], pm[4], m);
+    madc_wide_cc(E[6], E[7], pm[6], m);
+    O[7] = addc(O[7], 0);
+}
+
+// First row: V = a*b0, then reduce.
+template <class F> CPB_HD void first_row(u32* E, u32* O, const u32* a, u32 bi, const u32* pm) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        mul_wide(E[j], E[j + 1], a[j], bi);
+        mul_wide(O[j], O[j + 1], a[j + 1], bi);
+    }
+    redc_row<F>(E, O, pm);
+}
+
+// Later rows.  On entry `O` is the previous row's even accumulator (low limb zero) and `E`
+// the previous odd one: V/2^32 = E + O[1] + 2^32 * (O >> 64).  Adds a*bi, then reduces.
+template <class F> CPB_HD void next_row(u32* E, u32* O, const u32* a, u32 bi, const u32* pm) {
+    E[0] = add_cc(E[0], O[1]);
+    madc_wide_cc_from(O[0], O[1], a[1], bi, O[2], O[3]);
+    madc_wide_cc_from(O[2], O[3], a[3], bi, O[4], O[5]);
+    madc_wide_cc_from(O[4], O[5], a[5], bi, O[6], O[7]);
+    madc_wide_end(O[6], O[7], a[7], bi);
+    mad_wide_cc(E[0], E[1], a[0], bi);
+    madc_wide_cc(E[2], E[3], a[2], bi);
+    madc_wide_cc(E[4], E[5], a[4], bi);
+    madc_wide_cc(E[6], E[7], a[6], bi);
+    O[7] = addc(O[7], 0);
+    redc_row<F>(E, O, pm);
+}
+
+}  // namespace detail
+
+// r = a*b/R mod p, fully reduced.  a, b in [0,p).  r may alias a or b.
+template <class F> CPB_HD void fp_mul(u32* r, const u32* a, const u32* b, const u32* pm) {
+    u32 ev[8], od[8];
+    detail::first_row<F>(ev, od, a, b[0], pm);
+    detail::next_row<F>(od, ev, a, b[1], pm);
+    detail::next_row<F>(ev, od, a, b[2], pm);
+    detail::next_row<F>(od, ev, a, b[3], pm);
+    detail::next_row<F>(ev, od, a, b[4], pm);
+    detail::next_row<F>(od, ev, a, b[5], pm);
+    detail::next_row<F>(ev, od, a, b[6], pm);
+    detail::next_row<F>(od, ev, a, b[7], pm);
+    // last row used E = od (low limb zero), O = ev:  result = (od >> 32) + ev
+    r[0] = add_cc(ev[0], od[1]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r[i] = addc_cc(ev[i], od[i + 1]);
+    r[7] = addc(ev[7], 0);
+    fp_final_sub<F>(r);
+}
+
+template <class F> CPB_HD void fp_sqr(u32* r, const u32* a, const u32* pm) { fp_mul<F>(r, a, a, pm); }
+
+// ---------------------------------------------------------------------------------------
+// Lazy dot product: r = (sum_j a_j * b_j) / R mod p with ONE Montgomery reduction.
+// One CIOS pass adds all T partial products of a row before reducing it, so a T-term dot
+// product costs 8*(8T+8) wide multiply-adds instead of T*136.  The running value can reach
+// (T+1)*p*2^32, which for a 255-bit p no longer fits the 9 limbs of (E, O); X catches the
+// carries out of the top limb (it sits at 2^288 before the per-row shift, 2^256 after).
+// ---------------------------------------------------------------------------------------
+namespace detail {
+
+template <class F> CPB_HD void redc_row_x(u32* E, u32* O, u32& X, const u32* pm) {
+    u32 m = (F::NINV == 0xffffffffu) ? (0u - E[0]) : mul_lo(E[0], F::NINV);
+    mad_wide_cc(O[0], O[1], pm[1], m);
+    madc_wide_cc(O[2], O[3], pm[3], m);
+    madc_wide_cc(O[4], O[5], pm[5], m);
+    madc_wide_cc(O[6], O[7], pm[7], m);
+    X = addc(X, 0);
+    mad_wide_cc(E[0], E[1], pm[0], m);
+    madc_wide_cc(E[2], E[3], pm[2], m);
+    madc_wide_cc(E[4], E[5], pm[4], m);
+    madc_wide_cc(E[6], E[7], pm[6], m);
+    O[7] = addc_cc(O[7], 0);
+    X = addc(X, 0);
+}
+
+// V += a * bi   (no shift)
+CPB_HD void acc_row_x(u32* E, u32* O, u32& X, const u32* a, u32 bi) {
+    mad_wide_cc(O[0], O[1], a[1], bi);
+    madc_wide_cc(O[2], O[3], a[3], bi);
+    madc_wide_cc(O[4], O[5], a[5], bi);
+    madc_wide_cc(O[6], O[7], a[7], bi);
+    X = addc(X, 0);
+    mad_wide_cc(E[0], E[1], a[0], bi);
+    madc_wide_cc(E[2], E[3], a[2], bi);
+    madc_wide_cc(E[4], E[5], a[4], bi);
+    madc_wide_cc(E[6], E[7], a[6], bi);
+    O[7] = addc_cc(O[7], 0);
+    X = addc(X, 0);
+}
+
+// V = V/2^32 + a * bi  (E/O are the swapped accumulators, see next_row)
+CPB_HD void shift_acc_row_x(u32* E, u32* O, u32& X, const u32* a, u32 bi) {
+    E[0] = add_cc(E[0], O[1]);
+    madc_wide_cc_from(O[0], O[1], a[1], bi, O[2], O[3]);
+    madc_wide_cc_from(O[2], O[3], a[3], bi, O[4], O[5]);
+    madc_wide_cc_from(O[4], O[5], a[5], bi, O[6], O[7]);
+    madc_wide_end(O[6], O[7], a[7], bi);
+    O[7] += X;   // old overflow limb lands on the new top limb; cannot overflow (V/2^32 < 2^288)
+    mad_wide_cc(E[0], E[1], a[0], bi);
+    madc_wide_cc(E[2], E[3], a[2], bi);
+    madc_wide_cc(E[4], E[5], a[4], bi);
+    madc_wide_cc(E[6], E[7], a[6], bi);
+    O[7] = addc_cc(O[7], 0);
+    X = addc(0, 0);
+}
+
+// limb i (0..8) of p << k
+template <class F> CPB_HD constexpr u32 p_shl(int k, int i) {
+    return (u32)((((i < 8) ? (u64)F::P(i < 8 ? i : 0) : 0ull) << k) |
+                 ((i > 0 && k > 0) ? ((u64)F::P(i - 1) >> (32 - k)) : 0ull));
+}
+
+// r (9 limbs) < 2^(K+1) * p  ->  r[0..7] in [0,p)
+template <class F, int K> CPB_HD void reduce9(u32* r) {
+#pragma unroll
+    for (int k = K; k >= 0; k--) {
+        u32 t[9];
+        t[0] = sub_cc(r[0], p_shl<F>(k, 0));
+#pragma unroll
+        for (int i = 1; i < 9; i++) t[i] = subc_cc(r[i], p_shl<F>(k, i));
+        u32 borrow = subc(0, 0);
+#pragma unroll
+        for (int i = 0; i < 9; i++) r[i] = borrow ? r[i] : t[i];
+    }
+}
+
+template <class F, int T, int I> CPB_HD void dot_row(u32* E, u32* O, u32& X, const u32 (&a)[T][8], const u32* b, const u32* pm) {
+    // b: T constants of 8 limbs each (shared memory); this row uses limb I of each
+    if (I == 0) {
+        u32 bi = b[0];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            mul_wide(E[j], E[j + 1], a[0][j], bi);
+            mul_wide(O[j], O[j + 1], a[0][j + 1], bi);
+        }
+    } else {
+        shift_acc_row_x(E, O, X, a[0], b[I]);
+    }
+#pragma unroll
+    for (int t = 1; t < T; t++) acc_row_x(E, O, X, a[t], b[8 * t + I]);
+    redc_row_x<F>(E, O, X, pm);
+}
+
+}  // namespace detail
+
+// r = sum_{j<T} a[j] * b[j] / R mod p, fully reduced.  a[j], b[j] in [0,p).  r must not alias a.
+template <class F, int T> CPB_HD void fp_dot(u32* r, const u32 (&a)[T][8], const u32* b, const u32* pm) {
+    u32 ev[8], od[8], X = 0;
+    detail::dot_row<F, T, 0>(ev, od, X, a, b, pm);
+    detail::dot_row<F, T, 1>(od, ev, X, a, b, pm);
+    detail::dot_row<F, T, 2>(ev, od, X, a, b, pm);
+    detail::dot_row<F, T, 3>(od, ev, X, a, b, pm);
+    detail::dot_row<F, T, 4>(ev, od, X, a, b, pm);
+    detail::dot_row<F, T, 5>(od, ev, X, a, b, pm);
+    detail::dot_row<F, T, 6>(ev, od, X, a, b, pm);
+    detail::dot_row<F, T, 7>(od, ev, X, a, b, pm);
+    u32 w[9];
+    w[0] = add_cc(ev[0], od[1]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) w[i] = addc_cc(ev[i], od[i + 1]);
+    w[7] = addc_cc(ev[7], 0);
+    w[8] = addc(X, 0);
+    // value < (T+1)*p  <  2^(K+1)*p with K = floor(log2(T))
+    constexpr int K = (T >= 8) ? 3 : (T >= 4) ? 2 : (T >= 2) ? 1 : 0;
+    detail::reduce9<F, K>(w);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = w[i];
+}
+
+
+// x^alpha for the S-box.  5 and 17 get fixed addition chains; anything else falls back to
+// left-to-right square-and-multiply (alpha is uniform across the grid: no divergence).
+template <class F> CPB_HD void fp_pow_alpha(u32* x, u64 alpha, const u32* pm) {
+    u32 t[8];
+    if (alpha == 5) {
+        fp_sqr<F>(t, x, pm);
+        fp_sqr<F>(t, t, pm);
+        fp_mul<F>(x, t, x, pm);
+    } else if (alpha == 17) {
+        fp_sqr<F>(t, x, pm);
+        fp_sqr<F>(t, t, pm);
+        fp_sqr<F>(t, t, pm);
+        fp_sqr<F>(t, t, pm);
+        fp_mul<F>(x, t, x, pm);
+    } else if (alpha == 3) {
+        fp_sqr<F>(t, x, pm);
+        fp_mul<F>(x, t, x, pm);
+    } else {
+        if (alpha == 0) { fp_one<F>(x); return; }
+        int top = 63;
+        while (!((alpha >> top) & 1)) top--;
+        fp_copy(t, x);
+        for (int i = top - 1; i >= 0; i--) {
+            fp_sqr<F>(t, t, pm);
+            if ((alpha >> i) & 1) fp_mul<F>(t, t, x, pm);
+        }
+        fp_copy(x, t);
+    }
+}
+
+// Fermat inversion x^(p-2); 0 -> 0.  Only on cold paths (table build, batch normalisation).
+template <class F> CPB_HD void fp_inv(u32* r, const u32* x, const u32* pm) {
+    u32 acc[8], base[8], e[8];
+    fp_one<F>(acc);
+    fp_copy(base, x);
+    e[0] = sub_cc(F::P(0), 2u);
+#pragma unroll
+    for (int i = 1; i < 8; i++) e[i] = subc_cc(F::P(i), 0u);
+    // right-to-left binary exponentiation over the 256 bits of p-2
+#pragma unroll 1
+    for (int k = 0; k < 256; k++) {
+        u32 w = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) w = (k >> 5) == i ? e[i] : w;
+        if ((w >> (k & 31)) & 1) fp_mul<F>(acc, acc, base, pm);
+        fp_sqr<F>(base, base, pm);
+    }
+    fp_copy(r, acc);
+}
+
+}  // namespace cpb

@@ -1,0 +1,187 @@
+// poseidon.cuh -- the Poseidon permutation and the CRH / two-to-one evaluation built on it,
+// one hash per thread, whole state in registers.
+//
+// Device counterpart of PoseidonSponge::permute (R/sponge/poseidon/mod.rs:66-121) and of
+// crh::poseidon::{CRH::evaluate, TwoToOneCRH::compress} (R/crh/poseidon/mod.rs:30-40,66-79),
+// i.e. new sponge -> absorb (mod.rs:124-153) -> squeeze one native element (mod.rs:323-345).
+// Executes the schedule produced by host::derive_schedule (poseidon_host.hpp): same function,
+// sparse partial rounds.  Everything here is CPB_HD so tests/host can run the identical code
+// on the CPU (PTX primitives emulated) against the oracle before any GPU time is spent.
+#pragma once
+#include "fp.cuh"
+
+namespace cpb {
+
+struct PoseidonDev {
+    int t, rate, cap, rf, rp, sparse;
+    u64 alpha;
+    int off_c, off_m, off_mpre, off_cp0, off_pc, off_sp, off_arkp, off_mod, n_elems;
+    // Always 0.  Kernels add threadIdx.x * zero to the shared-memory address of every constant so
+    // that ptxas keeps multiplier operands in ordinary registers: values loaded from a
+    // warp-uniform address are promoted to uniform registers, and a multiply-add with a
+    // uniform-register factor is emitted as IMAD.X + IMAD.HI.U32.X instead of one IMAD.WIDE.U32.X.
+    int zero;
+};
+
+// Load one element (32 B, 16-byte aligned) as two 128-bit accesses.
+CPB_HD void ld_elem(u32* r, const u32* p) {
+#if defined(__CUDA_ARCH__)
+    uint4 a = *reinterpret_cast<const uint4*>(p);
+    uint4 b = *reinterpret_cast<const uint4*>(p + 4);
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+    r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+#else
+    for (int i = 0; i < 8; i++) r[i] = p[i];
+#endif
+}
+CPB_HD void st_elem(u32* p, const u32* r) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4*>(p) = make_uint4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<uint4*>(p + 4) = make_uint4(r[4], r[5], r[6], r[7]);
+#else
+    for (int i = 0; i < 8; i++) p[i] = r[i];
+#endif
+}
+
+template <class F, int T> CPB_HD void pos_add_vec(u32 (&s)[T][8], const u32* c) {
+#pragma unroll
+    for (int i = 0; i < T; i++) {
+        u32 k[8];
+        ld_elem(k, c + 8 * i);
+        fp_add<F>(s[i], s[i], k);
+    }
+}
+
+// (s0, s1, ..., s_{T-1}) <- (s1, ..., s_{T-1}, s0).  Lets a rolled loop visit every lane while
+// the state stays in registers (register files cannot be indexed dynamically); a rotation is
+// 8T moves against ~900 instructions of work per visit.
+template <int T> CPB_HD void pos_rotl(u32 (&s)[T][8]) {
+    u32 tmp[8];
+    fp_copy(tmp, s[0]);
+#pragma unroll
+    for (int i = 0; i + 1 < T; i++) fp_copy(s[i], s[i + 1]);
+    fp_copy(s[T - 1], tmp);
+}
+
+// x^alpha, left-to-right binary.  For the arkworks S-box exponents (3, 5, 17, 257 = 2^k+1)
+// this is k squarings and one multiplication -- the optimal chain -- from a single pair of
+// inlined multiplier bodies, which keeps the kernel's instruction footprint small.
+template <class F> CPB_HD void pos_sbox(u32* x, u64 alpha, int top_bit, const u32* pm) {
+    u32 t[8];
+    fp_copy(t, x);
+#pragma unroll 1
+    for (int i = top_bit - 1; i >= 0; i--) {
+        fp_sqr<F>(t, t, pm);
+        if ((alpha >> i) & 1) fp_mul<F>(t, t, x, pm);
+    }
+    fp_copy(x, t);
+}
+
+// The permutation, one rolled loop over all RF+RP rounds with a single instance of each
+// arithmetic body:  [add round constants] -> S-box on T lanes or lane 0 -> linear layer as
+// lazy dot products (T rows of a dense matrix, or the one dense row of the sparse form
+// followed by the rank-one column update).
+template <class F, int T> CPB_HD void pos_permute(u32 (&s)[T][8], const PoseidonDev& P, const u32* cs, const u32* pm) {
+    const int half = P.rf / 2, total = P.rf + P.rp;
+    int top_bit = 0;
+    for (int i = 63; i > 0; i--)
+        if ((P.alpha >> i) & 1) { top_bit = i; break; }
+    const bool alpha_zero = P.alpha == 0;
+#pragma unroll 1
+    for (int r = 0; r < total; r++) {
+        const bool full = r < half || r >= half + P.rp;
+        const int k = r - half;                       // partial-round index when !full
+        // --- round constants
+        if (full) {
+            const int fr = r < half ? r : r - P.rp;
+            pos_add_vec<F, T>(s, cs + 8 * (P.off_c + fr * T));
+        } else if (!P.sparse) {
+            pos_add_vec<F, T>(s, cs + 8 * (P.off_arkp + k * T));
+        } else if (k == 0) {
+            pos_add_vec<F, T>(s, cs + 8 * P.off_cp0);
+        }
+        // --- S-box
+        const int lanes = full ? T : 1;
+#pragma unroll 1
+        for (int j = 0; j < lanes; j++) {
+            if (alpha_zero) fp_one<F>(s[0]);
+            else pos_sbox<F>(s[0], P.alpha, top_bit, pm);
+            if (full) pos_rotl<T>(s);
+        }
+        // --- linear layer
+        const bool dense = full || !P.sparse;
+        const u32* rows = dense ? cs + 8 * ((full && r == half - 1) ? P.off_mpre : P.off_m)
+                                : cs + 8 * (P.off_sp + k * (2 * T - 1));
+        const int nrows = dense ? T : 1;
+        u32 n[T][8];
+#pragma unroll 1
+        for (int i = 0; i < nrows; i++) {
+            u32 d[8];
+            fp_dot<F, T>(d, s, rows + 8 * T * i, pm);
+            // shift d in at the end: after nrows == T iterations n[i] holds row i
+#pragma unroll
+            for (int q = 0; q + 1 < T; q++) fp_copy(n[q], n[q + 1]);
+            fp_copy(n[T - 1], d);
+        }
+        if (dense) {
+#pragma unroll
+            for (int i = 0; i < T; i++) fp_copy(s[i], n[i]);
+        } else {
+            // s_j += v_j * s_0 for j >= 1 (old s_0), then s_0 <- row product (+ next lane-0 constant)
+            const u32* v = rows + 8 * T;
+            if (T > 1) {
+#pragma unroll 1
+                for (int j = 1; j < T; j++) {
+                    u32 c[8], tmp[8];
+                    ld_elem(c, v + 8 * (j - 1));
+                    fp_mul<F>(tmp, s[0], c, pm);
+                    fp_add<F>(s[1], s[1], tmp);
+                    // rotate lanes 1..T-1
+                    fp_copy(tmp, s[1]);
+#pragma unroll
+                    for (int q = 1; q + 1 < T; q++) fp_copy(s[q], s[q + 1]);
+                    fp_copy(s[T - 1], tmp);
+                }
+            }
+            if (k + 1 < P.rp) {
+                u32 c[8];
+                ld_elem(c, cs + 8 * (P.off_pc + k + 1));
+                fp_add<F>(s[0], n[T - 1], c);
+            } else {
+                fp_copy(s[0], n[T - 1]);
+            }
+        }
+    }
+}
+
+// CRH::evaluate over `len` elements at `in` (contiguous, 32 B each) -> out (8 limbs).
+// Absorb semantics of mod.rs:124-153: fill `rate` lanes, permute while more input remains;
+// the squeeze then permutes once (so an empty input still costs one permutation).
+template <class F, int T> CPB_HD void pos_crh(u32* out, const u32* in, long len, const PoseidonDev& P, const u32* cs, const u32* pm) {
+    u32 s[T][8];
+#pragma unroll
+    for (int i = 0; i < T; i++) fp_zero(s[i]);
+    const int rate = P.rate, cap = P.cap;
+    const long nblocks = len <= rate ? 1 : (len + rate - 1) / rate;
+#pragma unroll 1
+    for (long b = 0; b < nblocks; b++) {
+        const long pos = b * rate;
+        const long rem = len - pos;
+        const int cnt = rem > rate ? rate : (int)rem;
+#pragma unroll
+        for (int i = 0; i < T; i++) {
+            int lane = i - cap;
+            if (lane >= 0 && lane < cnt) {
+                u32 e[8];
+                ld_elem(e, in + 8 * (pos + lane));
+                fp_add<F>(s[i], s[i], e);
+            }
+        }
+        pos_permute<F, T>(s, P, cs, pm);
+    }
+#pragma unroll
+    for (int i = 0; i < T; i++)
+        if (i == cap) fp_copy(out, s[i]);
+}
+
+}  // namespace cpb

@@ -1,0 +1,136 @@
+/*
+ * cpb200.h -- C ABI of libcpb200.so: B200-native (sm_100a) batched evaluation of the
+ * ark-crypto-primitives hot path (Poseidon CRH / two-to-one, Pedersen CRH / commitment,
+ * Merkle-tree build).  This is the drop-in boundary: plain pointers and sizes, no C++ or
+ * torch types.  A Rust shim crate binds these symbols and implements the reference traits on
+ * top of them (INTEGRATION.md shows the bindings).
+ *
+ * R below = /root/reference/crypto-primitives/src (arkworks-rs/crypto-primitives @ 6a770ebf).
+ *
+ * DATA LAYOUT.  A field element is 4 x uint64_t little-endian limbs in Montgomery form
+ * (R = 2^256), fully reduced -- the memory image of ark-ff's Fp<MontBackend<_,4>,4>
+ * (`BigInt<4>` in `.0.0`), so a `&[Fr]` can be passed without conversion.  A curve point is
+ * affine (x, y): 8 x uint64_t.  Byte inputs are plain uint8_t.  All arrays are dense, C order.
+ *
+ * POINTERS.  Functions without suffix take HOST pointers and perform the H2D/D2H copies
+ * themselves on the context's stream; `_dev` functions take DEVICE pointers (on the context's
+ * device) plus a CUDA stream handle (`cudaStream_t` passed as void*, NULL = default stream),
+ * launch asynchronously and do not synchronise.
+ *
+ * ERRORS.  Every function returns a cpb_status.  Nothing panics/throws across the ABI; the
+ * shim maps codes back to the reference's behaviour (R/lib.rs:46-52 `Error`, and the panics at
+ * R/crh/pedersen/mod.rs:82-89, R/merkle_tree/mod.rs:430-433).  cpb_last_error() returns a
+ * thread-local description of the last failure.  There is NO CPU fallback: without a usable
+ * sm_100 device every compute entry point fails with CPB_NO_DEVICE / CPB_CUDA_ERROR.
+ *
+ * THREADING.  A context is immutable after creation and may be used from several host
+ * threads concurrently (reference: `Parameters: Sync`, R/crh/mod.rs:21); host-pointer calls
+ * serialise on an internal mutex that guards the context's staging buffers.
+ */
+#ifndef CPB200_H
+#define CPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cpb_status {
+    CPB_OK = 0,
+    CPB_BAD_LENGTH = 1,   /* R/crh/pedersen/mod.rs:82-89 "incorrect input length" panic; Error::IncorrectInputLength */
+    CPB_BAD_PARAMS = 2,   /* PoseidonConfig::new asserts, R/sponge/poseidon/mod.rs:198-206; generator-count assert R/crh/pedersen/mod.rs:101-109 */
+    CPB_NOT_POW2 = 3,     /* R/merkle_tree/mod.rs:430-433 */
+    CPB_CUDA_ERROR = 4,
+    CPB_NO_DEVICE = 5,
+    CPB_UNSUPPORTED = 6,
+    CPB_NULL_POINTER = 7
+} cpb_status;
+
+typedef enum cpb_field {
+    CPB_BLS12_381_FR = 0, /* the reference's test field, R/sponge/test.rs:5-12 */
+    CPB_BN254_FR = 1,
+    CPB_JUBJUB_FR = 2,    /* ark_ed_on_bls12_381::Fr, R/merkle_tree/tests/mod.rs:195 */
+    CPB_BLS12_377_FR = 3  /* R/crh/poseidon/constraints.rs:133-190 */
+} cpb_field;
+
+typedef enum cpb_curve {
+    CPB_JUBJUB = 0        /* ark_ed_on_bls12_381::EdwardsProjective, base field = BLS12-381 Fr */
+} cpb_curve;
+
+typedef struct cpb_poseidon_ctx cpb_poseidon_ctx;
+typedef struct cpb_pedersen_ctx cpb_pedersen_ctx;
+
+const char* cpb_last_error(void);
+int cpb_version(void);
+/* Number of visible CUDA devices with compute capability 10.x (0 when none / no driver). */
+int cpb_device_count(void);
+
+/* ---- fields ----------------------------------------------------------------------------- */
+/* Modulus as 4 LE limbs.  (ark-ff `F::MODULUS`.) */
+cpb_status cpb_field_modulus(int field_id, uint64_t out[4]);
+/* Canonical little-endian integers (< 2^256; reduced mod p) <-> Montgomery limbs, on `device`.
+ * Convenience for non-Rust callers; ark-ff callers already hold Montgomery limbs. */
+cpb_status cpb_field_to_montgomery(int field_id, int device, const uint64_t* in, uint64_t* out, size_t n);
+cpb_status cpb_field_from_montgomery(int field_id, int device, const uint64_t* in, uint64_t* out, size_t n);
+
+/* ---- Poseidon --------------------------------------------------------------------------- */
+/* find_poseidon_ark_and_mds, R/sponge/poseidon/traits.rs:105-146 (Grain LFSR of
+ * R/sponge/poseidon/grain_lfsr.rs).  ark_out: (full+partial) x (rate+1) elements, mds_out:
+ * (rate+1)^2 elements, Montgomery.  Host-only, once per parameter set. */
+cpb_status cpb_poseidon_find_ark_and_mds(int field_id, uint64_t prime_bits, int rate, int full_rounds,
+                                         int partial_rounds, int skip_matrices, uint64_t* ark_out,
+                                         uint64_t* mds_out);
+/* PoseidonDefaultConfigField::get_default_poseidon_parameters, traits.rs:59-103, with the entry
+ * tables of R/sponge/test.rs:13-32 (rate 2..8, capacity 1).  Writes the shape; a second call of
+ * cpb_poseidon_find_ark_and_mds with that shape yields ark/mds. */
+cpb_status cpb_poseidon_default_entry(int rate, int optimized_for_weights, uint64_t* alpha, int* full_rounds,
+                                      int* partial_rounds, int* skip_matrices);
+
+/* PoseidonConfig::new, R/sponge/poseidon/mod.rs:189-217.  ark: (full+partial) x t, mds: t x t
+ * (t = rate+capacity), Montgomery limbs, copied.  Uploads the device round schedule. */
+cpb_status cpb_poseidon_ctx_create(int field_id, int rate, int capacity, int full_rounds, int partial_rounds,
+                                   uint64_t alpha, const uint64_t* ark, const uint64_t* mds, int device,
+                                   cpb_poseidon_ctx** out);
+void cpb_poseidon_ctx_destroy(cpb_poseidon_ctx* ctx);
+/* 1 when the partial rounds run in sparse form, 0 for the dense fallback (same results). */
+int cpb_poseidon_ctx_is_sparse(const cpb_poseidon_ctx* ctx);
+
+/* n independent permutations of t-element states: PoseidonSponge::permute, mod.rs:98-121. */
+cpb_status cpb_poseidon_permute_batch(cpb_poseidon_ctx* ctx, const uint64_t* states_in, uint64_t* states_out, size_t n);
+cpb_status cpb_poseidon_permute_batch_dev(cpb_poseidon_ctx* ctx, const uint64_t* states_in, uint64_t* states_out,
+                                          size_t n, void* stream);
+
+/* n x crh::poseidon::CRH::evaluate (R/crh/poseidon/mod.rs:30-40): input i is the `len` elements
+ * at in + 4*len*i; out[i] one element.  len == 0 is allowed (one permutation of the zero state). */
+cpb_status cpb_poseidon_crh_batch(cpb_poseidon_ctx* ctx, const uint64_t* in, size_t len, uint64_t* out, size_t n);
+cpb_status cpb_poseidon_crh_batch_dev(cpb_poseidon_ctx* ctx, const uint64_t* in, size_t len, uint64_t* out, size_t n,
+                                      void* stream);
+
+/* n x crh::poseidon::TwoToOneCRH::compress / evaluate (mod.rs:58-79): pairs[i] = (left, right). */
+cpb_status cpb_poseidon_compress_batch(cpb_poseidon_ctx* ctx, const uint64_t* pairs, uint64_t* out, size_t n);
+cpb_status cpb_poseidon_compress_batch_dev(cpb_poseidon_ctx* ctx, const uint64_t* pairs, uint64_t* out, size_t n,
+                                           void* stream);
+
+/* ---- Merkle tree, field leaves ---------------------------------------------------------- */
+/* MerkleTree::new (R/merkle_tree/mod.rs:411-422) for Config{Leaf=[F], LeafDigest=InnerDigest=F,
+ * IdentityDigestConverter, LeafHash=poseidon::CRH, TwoToOneHash=poseidon::TwoToOneCRH}
+ * (R/merkle_tree/tests/mod.rs:198-206).  leaves: n x leaf_len elements.  Outputs the reference's
+ * two arrays: leaf_nodes[n], non_leaf_nodes[n-1] in heap order (root at 0; children of i at
+ * 2i+1, 2i+2; mod.rs:383-395).  n must be a power of two > 1 (else CPB_NOT_POW2). */
+cpb_status cpb_merkle_poseidon_build(cpb_poseidon_ctx* leaf_ctx, cpb_poseidon_ctx* node_ctx, const uint64_t* leaves,
+                                     size_t leaf_len, size_t n, uint64_t* leaf_nodes, uint64_t* non_leaf_nodes);
+cpb_status cpb_merkle_poseidon_build_dev(cpb_poseidon_ctx* leaf_ctx, cpb_poseidon_ctx* node_ctx,
+                                         const uint64_t* leaves, size_t leaf_len, size_t n, uint64_t* leaf_nodes,
+                                         uint64_t* non_leaf_nodes, void* stream);
+/* MerkleTree::new_with_leaf_digest (mod.rs:424-523): inner levels only. */
+cpb_status cpb_merkle_poseidon_from_digests(cpb_poseidon_ctx* node_ctx, const uint64_t* leaf_digests, size_t n,
+                                            uint64_t* non_leaf_nodes);
+cpb_status cpb_merkle_poseidon_from_digests_dev(cpb_poseidon_ctx* node_ctx, const uint64_t* leaf_digests, size_t n,
+                                                uint64_t* non_leaf_nodes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPB200_H */

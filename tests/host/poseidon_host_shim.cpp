@@ -1,0 +1,76 @@
+// CPU build of the device Poseidon code path (crypto_primitives_b200/csrc/poseidon.cuh with the
+// PTX primitives emulated) driven by the product's own host-side schedule derivation
+// (poseidon_host.hpp).  Lets tests/test_poseidon_host.py check, without a GPU, that the sparse
+// round schedule + device permutation reproduce the oracle bit-for-bit.  Not part of the product.
+#include "../../crypto_primitives_b200/csrc/poseidon.cuh"
+#include "../../crypto_primitives_b200/csrc/poseidon_host.hpp"
+#include <cstring>
+using namespace cpb;
+
+static PoseidonDev to_dev(const host::PoseidonSchedule& S) {
+    PoseidonDev D;
+    D.t = S.t; D.rate = S.rate; D.cap = S.capacity; D.rf = S.rf; D.rp = S.rp; D.sparse = S.sparse; D.alpha = S.alpha;
+    D.off_c = S.off_c; D.off_m = S.off_m; D.off_mpre = S.off_mpre; D.off_cp0 = S.off_cp0; D.off_pc = S.off_pc;
+    D.off_sp = S.off_sp; D.off_arkp = S.off_arkp; D.off_mod = S.off_mod; D.n_elems = S.n_elems; D.zero = 0;
+    return D;
+}
+
+template <class F, int T>
+static void run(const PoseidonDev& D, const u32* cs, const u32* in, long len, long n, u32* out) {
+    u32 pm[8];
+    ld_elem(pm, cs + 8 * D.off_mod);
+    for (long i = 0; i < n; i++) pos_crh<F, T>(out + 8 * i, in + 8 * len * i, len, D, cs, pm);
+}
+
+template <class F>
+static int run_t(const PoseidonDev& D, const u32* cs, const u32* in, long len, long n, u32* out) {
+    switch (D.t) {
+        case 2: run<F, 2>(D, cs, in, len, n, out); return 0;
+        case 3: run<F, 3>(D, cs, in, len, n, out); return 0;
+        case 4: run<F, 4>(D, cs, in, len, n, out); return 0;
+        case 5: run<F, 5>(D, cs, in, len, n, out); return 0;
+        case 9: run<F, 9>(D, cs, in, len, n, out); return 0;
+    }
+    return 1;
+}
+
+// returns: -1 error, else the `sparse` flag of the derived schedule
+extern "C" int host_poseidon_crh(int field, int rate, int cap, int rf, int rp, unsigned long long alpha,
+                                 const uint64_t* ark, const uint64_t* mds, int allow_sparse,
+                                 const uint64_t* in, long len, long n, uint64_t* out) {
+    const uint64_t* mod = host::field_modulus(field);
+    if (!mod) return -1;
+    host::Field F(mod);
+    host::PoseidonParams P;
+    P.rate = rate; P.capacity = cap; P.full_rounds = rf; P.partial_rounds = rp; P.alpha = alpha;
+    int t = rate + cap;
+    P.ark.resize((size_t)(rf + rp) * t);
+    P.mds.resize((size_t)t * t);
+    memcpy(P.ark.data(), ark, P.ark.size() * 32);
+    memcpy(P.mds.data(), mds, P.mds.size() * 32);
+    host::PoseidonSchedule S = host::derive_schedule(F, P, allow_sparse != 0);
+    PoseidonDev D = to_dev(S);
+    const u32* cs = reinterpret_cast<const u32*>(S.consts.data());
+    const u32* i32 = reinterpret_cast<const u32*>(in);
+    u32* o32 = reinterpret_cast<u32*>(out);
+    int rc = 1;
+    switch (field) {
+        case 0: rc = run_t<Bls12_381_Fr>(D, cs, i32, len, n, o32); break;
+        case 1: rc = run_t<Bn254_Fr>(D, cs, i32, len, n, o32); break;
+        case 2: rc = run_t<Jubjub_Fr>(D, cs, i32, len, n, o32); break;
+        case 3: rc = run_t<Bls12_377_Fr>(D, cs, i32, len, n, o32); break;
+    }
+    return rc ? -1 : S.sparse;
+}
+
+// find_poseidon_ark_and_mds on the product's host code; outputs Montgomery limbs.
+extern "C" int host_poseidon_find_params(int field, int rate, int rf, int rp, int skip, uint64_t* ark, uint64_t* mds) {
+    const uint64_t* mod = host::field_modulus(field);
+    if (!mod) return -1;
+    host::Field F(mod);
+    host::FeVec a, m;
+    host::find_poseidon_ark_and_mds(F, (uint64_t)F.bits, rate, rf, rp, skip, a, m);
+    memcpy(ark, a.data(), a.size() * 32);
+    memcpy(mds, m.data(), m.size() * 32);
+    return 0;
+}

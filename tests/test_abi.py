@@ -1,0 +1,69 @@
+"""The C-ABI library loads and exports every symbol include/cpb200.h declares; host-only entry
+points (parameter generation, argument validation) behave like the reference.  No GPU needed."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, kats
+import crypto_primitives_b200 as cp
+from crypto_primitives_b200 import _native as N
+from oracle import fields as OF
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    hdr = open(os.path.join(ROOT, "include", "cpb200.h")).read()
+    declared = set(re.findall(r"\b(cpb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = C.CDLL(N.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in cpb200.h but not exported"
+    assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
+
+
+def test_moduli():
+    for f in cp.FIELDS.values():
+        assert f.modulus == OF.MODULI[f.name]
+
+
+def test_default_parameters_match_reference_kats():
+    K = kats()["default_params"]
+    f = cp.BLS12_381_FR
+    for weights in (False, True):
+        for rate in range(2, 9):
+            cfg = cp.get_default_poseidon_parameters(f, rate, weights)
+            e = K["weights" if weights else "constraints"][str(rate)]
+            assert f.to_ints(cfg.ark[0, 0])[0] == int(e["ark00"])
+            assert f.to_ints(cfg.mds[0, 0])[0] == int(e["mds00"])
+            assert cfg.capacity == 1 and cfg.rate == rate
+    assert cp.get_default_poseidon_parameters(f, 9, False) is None          # traits.rs:102 -> None
+    assert cp.get_default_poseidon_parameters(f, 1, False) is None
+
+
+def test_find_ark_and_mds_rejects_wrong_bit_size():
+    a = np.zeros((39, 3, 4), dtype=np.uint64)
+    m = np.zeros((3, 3, 4), dtype=np.uint64)
+    st = N.lib.cpb_poseidon_find_ark_and_mds(0, 254, 2, 8, 31, 0, a.ctypes.data_as(N.u64p), m.ctypes.data_as(N.u64p))
+    assert st == N.CPB_BAD_PARAMS and b"MODULUS_BIT_SIZE" in N.lib.cpb_last_error()
+
+
+def test_ctx_create_validates_before_touching_the_gpu():
+    out = N.vp()
+    a = np.zeros((39, 3, 4), dtype=np.uint64)
+    m = np.zeros((3, 3, 4), dtype=np.uint64)
+    assert N.lib.cpb_poseidon_ctx_create(9, 2, 1, 8, 31, 17, a.ctypes.data_as(N.u64p), m.ctypes.data_as(N.u64p), 0, C.byref(out)) == N.CPB_BAD_PARAMS
+    assert N.lib.cpb_poseidon_ctx_create(0, 0, 1, 8, 31, 17, a.ctypes.data_as(N.u64p), m.ctypes.data_as(N.u64p), 0, C.byref(out)) == N.CPB_BAD_PARAMS
+    bad = a.copy()
+    bad[0, 0] = np.uint64(0xFFFFFFFFFFFFFFFF)                               # not reduced
+    assert N.lib.cpb_poseidon_ctx_create(0, 2, 1, 8, 31, 17, bad.ctypes.data_as(N.u64p), m.ctypes.data_as(N.u64p), 0, C.byref(out)) == N.CPB_BAD_PARAMS
+
+
+@pytest.mark.skipif(N.lib.cpb_device_count() > 0, reason="a B200 is present")
+def test_no_cpu_fallback_without_device():
+    """Without a GPU the compute path must fail loudly, never fall back."""
+    cfg = cp.get_default_poseidon_parameters(cp.BLS12_381_FR, 2, False)
+    with pytest.raises(N.CpbError) as e:
+        cp.crh_poseidon.CRH.evaluate(cfg, cp.BLS12_381_FR.elements([0, 1, 2]))
+    assert e.value.status in (N.CPB_NO_DEVICE, N.CPB_CUDA_ERROR)

@@ -1,0 +1,113 @@
+"""GPU parity tests for the field-leaf Merkle build (MerkleTree::new, R/merkle_tree/mod.rs:411-523)
+and the proof / update surface the reference's own tests exercise (R/merkle_tree/tests/mod.rs:185-310)."""
+import numpy as np
+import pytest
+
+from helpers import kats, oracle_config, product_config, synth_elems
+import crypto_primitives_b200 as cp
+from crypto_primitives_b200.merkle_tree import MerkleTree
+from oracle import cref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("which,n,L", [("jubjub_merkle_fixture", 128, 3), ("bls_default_r2", 2, 2), ("bls_default_r2", 4, 1),
+                                       ("bls_default_r2", 4096, 2), ("bn254_r2", 1 << 14, 2), ("bls_sponge_fixture", 64, 5)])
+def test_build_matches_oracle_arrays(which, n, L):
+    _, ocfg = oracle_config(which)
+    cfg = product_config(which)
+    leaves = synth_elems(300 + n, (n, L), ocfg.p)
+    O = cref.Poseidon(ocfg)
+    exp_leaf, exp_nodes = cref.poseidon_merkle(O, O, leaves, threads=8)
+    t = MerkleTree.new(cfg, cfg, leaves)
+    assert np.array_equal(t.leaf_nodes, exp_leaf)
+    assert np.array_equal(t.non_leaf_nodes, exp_nodes)            # heap order, root at 0
+    assert t.height() == n.bit_length() and np.array_equal(t.root(), exp_nodes[0])
+
+
+def test_reference_field_mt_scenario():
+    """field_mt_tests::good_root_test (R/merkle_tree/tests/mod.rs:289-309): 128 leaves x 3 elements over
+    Jubjub Fr with the fixed parameters of test_utils.rs; proofs, multiproof, wrong root, updates."""
+    _, ocfg = oracle_config("jubjub_merkle_fixture")
+    cfg = product_config("jubjub_merkle_fixture")
+    f = cfg.field
+    leaves = synth_elems(9, (128, 3), ocfg.p)
+    tree = MerkleTree.new(cfg, cfg, leaves)
+    root = tree.root()
+    for i in (0, 1, 2, 63, 64, 127):
+        assert tree.generate_proof(i).verify(cfg, cfg, root, leaves[i])
+    mp = tree.generate_multi_proof(range(128))
+    assert mp.verify(cfg, cfg, root, leaves)
+    wrong = f.elements([(f.to_ints(root)[0] + 1) % f.modulus])[0]              # root + F::one()
+    assert not tree.generate_proof(0).verify(cfg, cfg, wrong, leaves[0])
+    assert not mp.verify(cfg, cfg, wrong, leaves)
+    upd = synth_elems(10, (5, 3), ocfg.p)
+    for k, i in enumerate((2, 3, 5, 111, 127)):
+        tree.update(i, upd[k])
+        leaves[i] = upd[k]
+    O = cref.Poseidon(ocfg)
+    exp_leaf, exp_nodes = cref.poseidon_merkle(O, O, leaves, threads=8)
+    assert np.array_equal(tree.non_leaf_nodes, exp_nodes) and np.array_equal(tree.leaf_nodes, exp_leaf)
+    root = tree.root()
+    for i in (0, 3, 111, 127):
+        assert tree.generate_proof(i).verify(cfg, cfg, root, leaves[i])
+    assert tree.check_update(7, upd[0], root) is False                          # tree untouched on failure
+    assert np.array_equal(tree.non_leaf_nodes, exp_nodes)
+
+
+def test_multiproof_prefix_lengths_kat():
+    cfg = product_config("bls_default_r2")
+    _, ocfg = oracle_config("bls_default_r2")
+    tree = MerkleTree.new(cfg, cfg, synth_elems(4, (8, 2), ocfg.p))
+    mp = tree.generate_multi_proof(range(8))
+    assert mp.auth_paths_prefix_lenghts == kats()["multiproof_prefix_lengths_8_leaves"]["value"]
+
+
+def test_blank_and_new_with_leaf_digest():
+    cfg = product_config("bls_default_r2")
+    _, ocfg = oracle_config("bls_default_r2")
+    O = cref.Poseidon(ocfg)
+    t = MerkleTree.blank(cfg, cfg, 5)                                           # 16 zero digests
+    z = np.zeros((16, 4), dtype=np.uint64)
+    lvl = z
+    while lvl.shape[0] > 1:
+        lvl = O.compress_batch(lvl.reshape(-1, 2, 4))
+    assert np.array_equal(t.root(), lvl[0]) and t.height() == 5
+    d = synth_elems(6, (32,), ocfg.p)
+    t2 = MerkleTree.new_with_leaf_digest(cfg, cfg, d)
+    lvl = d
+    while lvl.shape[0] > 1:
+        lvl = O.compress_batch(lvl.reshape(-1, 2, 4))
+    assert np.array_equal(t2.root(), lvl[0])
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 24])
+def test_not_power_of_two_is_rejected(n):
+    """R/merkle_tree/mod.rs:430-433 asserts; the ABI returns CPB_NOT_POW2, the mirror raises."""
+    cfg = product_config("bls_default_r2")
+    with pytest.raises(ValueError):
+        MerkleTree.new(cfg, cfg, np.zeros((n, 2, 4), dtype=np.uint64))
+
+
+def test_full_size_tree_properties():
+    """BASELINE config 2 (2^20 leaves, BLS12-381 Fr): the oracle recomputes the top levels and sampled
+    bottom nodes; every level must be the compression of the level below (checked via the oracle on
+    random positions), and the build must be deterministic."""
+    _, ocfg = oracle_config("bls_default_r2")
+    cfg = product_config("bls_default_r2")
+    n = 1 << 20
+    leaves = synth_elems(2, (n, 2), ocfg.p)
+    t = MerkleTree.new(cfg, cfg, leaves)
+    O = cref.Poseidon(ocfg)
+    rng = np.random.default_rng(1)
+    li = rng.choice(n, 256, replace=False)
+    assert np.array_equal(t.leaf_nodes[li], O.crh_batch(leaves[li], threads=8))
+    nodes = t.non_leaf_nodes
+    idx = np.concatenate([np.arange(0, 1023), rng.choice(n // 2 - 1, 512, replace=False)])   # top 10 levels + samples
+    kids = np.stack([nodes[2 * idx + 1], nodes[2 * idx + 2]], axis=1)
+    assert np.array_equal(nodes[idx], O.compress_batch(kids, threads=8))
+    bi = rng.choice(n // 2, 256, replace=False)                                           # bottom inner level
+    kids = np.stack([t.leaf_nodes[2 * bi], t.leaf_nodes[2 * bi + 1]], axis=1)
+    assert np.array_equal(nodes[n // 2 - 1 + bi], O.compress_batch(kids, threads=8))
+    t2 = MerkleTree.new(cfg, cfg, leaves)
+    assert np.array_equal(t2.non_leaf_nodes, nodes)

@@ -1,0 +1,93 @@
+"""The device Poseidon code (csrc/poseidon.cuh: sparse-round schedule, lazy dot products, absorb
+loop) compiled for the CPU with emulated PTX, driven by the product's own schedule derivation
+(csrc/poseidon_host.hpp), against the oracle.  Bit-exact, both the sparse and the dense schedule."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+from helpers import ALL_CONFIGS, build_host_shim, oracle_config, synth_elems
+from oracle import cref, fields as OF, poseidon as OP
+
+u64p = C.POINTER(C.c_uint64)
+FID = {"bls12_381_fr": 0, "bn254_fr": 1, "jubjub_fr": 2, "bls12_377_fr": 3}
+
+
+@pytest.fixture(scope="module")
+def shim():
+    return build_host_shim("poseidon_host_shim")
+
+
+def _P(a):
+    return a.ctypes.data_as(u64p)
+
+
+def run(shim, fid, cfg, inp, allow_sparse):
+    p = cfg.p
+    ark = cref.ints_to_mont([x for r in cfg.ark for x in r], p)
+    mds = cref.ints_to_mont([x for r in cfg.mds for x in r], p)
+    n, L = inp.shape[0], inp.shape[1]
+    out = np.zeros((n, 4), dtype=np.uint64)
+    rc = shim.host_poseidon_crh(fid, cfg.rate, cfg.capacity, cfg.full_rounds, cfg.partial_rounds, C.c_ulonglong(cfg.alpha),
+                                _P(ark), _P(mds), allow_sparse, _P(np.ascontiguousarray(inp)), C.c_long(L), C.c_long(n), _P(out))
+    assert rc >= 0
+    return rc, out
+
+
+def check(shim, fid, cfg, Ls=(0, 1, 2, 3, 5), n=8, expect_sparse=None):
+    O = cref.Poseidon(cfg)
+    for L in Ls:
+        inp = np.ascontiguousarray(synth_elems(100 + L, (n, max(L, 1)), cfg.p)[:, :L])
+        if L:
+            inp[0, :] = cref.ints_to_mont([cfg.p - 1] * L, cfg.p)
+        exp = O.crh_batch(inp)
+        for sp in (1, 0):
+            rc, out = run(shim, fid, cfg, inp, sp)
+            assert (out == exp).all(), (L, sp)
+            if sp and expect_sparse is not None:
+                assert rc == expect_sparse
+
+
+@pytest.mark.parametrize("which", ALL_CONFIGS)
+def test_named_configs(shim, which):
+    fname, cfg = oracle_config(which)
+    check(shim, FID[fname], cfg, expect_sparse=1)
+
+
+@pytest.mark.parametrize("rate", [1, 3, 4, 8])
+def test_other_widths(shim, rate):
+    p = OF.BLS12_381_FR
+    cfg = OP.get_default_poseidon_parameters(p, rate, False) if rate > 1 else None
+    if cfg is None:
+        rng = OF.SplitMix64(1)
+        cfg = OP.PoseidonConfig(p, 4, 3, 17, [[rng.field(p) for _ in range(2)] for _ in range(7)],
+                                [[rng.field(p) for _ in range(2)] for _ in range(2)], 1, 1)
+    check(shim, 0, cfg, Ls=(0, 1, rate, rate + 1, 2 * rate + 1), n=4)
+
+
+def test_adversarial_shapes(shim):
+    """all-(p-1) matrices (largest lazy accumulations; singular -> dense fallback), capacity 2,
+    no partial rounds, odd exponents."""
+    rnd = random.Random(3)
+    for p, fid in ((OF.BLS12_381_FR, 0), (OF.BN254_FR, 1)):
+        for rate, cap, rf, rp, alpha, maxed in ((2, 1, 8, 5, 5, True), (2, 1, 2, 0, 3, False), (3, 2, 4, 2, 7, False),
+                                                (2, 1, 8, 4, 31, False)):
+            t = rate + cap
+            ark = [[rnd.choice([p - 1, rnd.randrange(p)]) for _ in range(t)] for _ in range(rf + rp)]
+            mds = [[p - 1] * t for _ in range(t)] if maxed else [[rnd.randrange(p) for _ in range(t)] for _ in range(t)]
+            check(shim, fid, OP.PoseidonConfig(p, rf, rp, alpha, ark, mds, rate, cap), Ls=(0, 1, 2, 4), n=4,
+                  expect_sparse=0 if (maxed or rp == 0) else 1)
+
+
+def test_product_param_generation_matches_oracle(shim):
+    """find_poseidon_ark_and_mds in the product's host code == oracle == reference KATs."""
+    for fid, p, bits, rate, rf, rp in ((0, OF.BLS12_381_FR, 255, 2, 8, 31), (1, OF.BN254_FR, 254, 2, 8, 57),
+                                       (0, OF.BLS12_381_FR, 255, 4, 8, 56)):
+        t = rate + 1
+        a = np.zeros(((rf + rp) * t, 4), dtype=np.uint64)
+        m = np.zeros((t * t, 4), dtype=np.uint64)
+        assert shim.host_poseidon_find_params(fid, rate, rf, rp, 0, _P(a), _P(m)) == 0
+        ark, mds = OP.find_poseidon_ark_and_mds(p, bits, rate, rf, rp, 0)
+        assert cref.mont_to_ints(a, p) == [x for r in ark for x in r]
+        assert cref.mont_to_ints(m, p) == [x for r in mds for x in r]
