@@ -29,6 +29,8 @@ SIGNATURES = {
     "cpb_poseidon_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, u64p, u64p, C.c_int, C.POINTER(vp)]),
     "cpb_poseidon_ctx_destroy": (None, [vp]),
     "cpb_poseidon_ctx_is_sparse": (C.c_int, [vp]),
+    "cpb_poseidon_ctx_field": (C.c_int, [vp]),
+    "cpb_poseidon_ctx_device": (C.c_int, [vp]),
     "cpb_poseidon_permute_batch": (C.c_int, [vp, u64p, u64p, C.c_size_t]),
     "cpb_poseidon_permute_batch_dev": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
     "cpb_poseidon_crh_batch": (C.c_int, [vp, u64p, C.c_size_t, u64p, C.c_size_t]),
@@ -39,6 +41,20 @@ SIGNATURES = {
     "cpb_merkle_poseidon_build_dev": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_size_t, vp, vp, vp]),
     "cpb_merkle_poseidon_from_digests": (C.c_int, [vp, u64p, C.c_size_t, u64p]),
     "cpb_merkle_poseidon_from_digests_dev": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
+    "cpb_pedersen_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_int, u64p, C.c_size_t, u64p, C.c_int, C.POINTER(vp)]),
+    "cpb_pedersen_ctx_destroy": (None, [vp]),
+    "cpb_pedersen_crh_batch": (C.c_int, [vp, u8p, C.c_size_t, C.c_size_t, u64p, C.c_size_t]),
+    "cpb_pedersen_crh_batch_dev": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp, C.c_size_t, vp]),
+    "cpb_pedersen_crh_x_batch": (C.c_int, [vp, u8p, C.c_size_t, C.c_size_t, u64p, C.c_size_t]),
+    "cpb_pedersen_crh_x_batch_dev": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp, C.c_size_t, vp]),
+    "cpb_pedersen_two_to_one_batch": (C.c_int, [vp, u64p, u64p, C.c_size_t]),
+    "cpb_pedersen_two_to_one_batch_dev": (C.c_int, [vp, vp, vp, C.c_size_t, vp, vp]),
+    "cpb_pedersen_commit_batch": (C.c_int, [vp, u8p, C.c_size_t, C.c_size_t, u8p, u64p, C.c_size_t]),
+    "cpb_pedersen_commit_batch_dev": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp, vp, C.c_size_t, vp]),
+    "cpb_merkle_pedersen_build": (C.c_int, [vp, vp, u8p, C.c_size_t, C.c_size_t, u64p, u64p]),
+    "cpb_merkle_pedersen_build_dev": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, vp, vp]),
+    "cpb_merkle_mixed_build": (C.c_int, [vp, vp, u8p, C.c_size_t, C.c_size_t, u64p, u64p]),
+    "cpb_merkle_mixed_build_dev": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, vp]),
 }
 
 
@@ -51,7 +67,7 @@ class CpbError(RuntimeError):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m crypto_primitives_b200._build` "
+            f"{LIB_PATH} is missing: build it with `python crypto_primitives_b200/_build.py` "
             "(nvcc, sm_100a).  crypto_primitives_b200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():

@@ -1,0 +1,610 @@
+// cpb_pedersen.cu -- CUDA kernels + C-ABI for Pedersen CRH / two-to-one / commitment over a
+// twisted-Edwards curve and the Merkle builds that use them (include/cpb200.h).
+//
+// Kernels (sm_100a, integer pipe):
+//   k_pedersen_table   once per context: 256 subset sums per 8-bit chunk of the flattened generator
+//                      list, normalised to affine-Niels entries (96 B each).
+//   k_pedersen_hash    one hash per thread: for every input byte, one table lookup + one 7M mixed
+//                      addition; the chunk's 24 KB table slice is staged in shared memory by TMA
+//                      bulk copies, double-buffered against the additions; the final projective ->
+//                      affine conversion shares one field inversion per warp (shuffle product tree).
+//   k_points_to_bytes  serialize_uncompressed of child digests for TwoToOneCRH::compress
+//                      (R/crh/pedersen/mod.rs:187-197, R/macros.rs:3-13): canonical x || y.
+#include <vector>
+
+#include "common.cuh"
+#include "hostfp.hpp"
+#include "pedersen.cuh"
+
+namespace cpb {
+
+constexpr int kPedBlock = 256;
+constexpr int kEntryWords = 24;                    // 3 field elements
+constexpr int kChunkWords = 256 * kEntryWords;     // one 8-bit chunk: 24576 B
+constexpr unsigned kChunkBytes = kChunkWords * 4;
+
+struct PedersenDev {
+    int n_in_chunks;     // floor(WINDOW_SIZE*NUM_WINDOWS / 8): input bytes that can carry set bits
+    int n_rand_chunks;   // ceil(#randomness generators / 8), 0 without commitment parameters
+    int zero;            // always 0 (see PoseidonDev::zero)
+};
+
+// consts layout (u32 words): [0..8) modulus limbs, [8..16) 2d (Montgomery), [16..24) d (Montgomery)
+template <class F>
+__global__ void __launch_bounds__(256)
+k_pedersen_table(const u32* __restrict__ consts, const u32* __restrict__ gens_xy, int n_gens, int n_chunks,
+                 u32* __restrict__ table, int zero) {
+    long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long)n_chunks * 256) return;
+    const int chunk = (int)(e >> 8), mask = (int)(e & 255);
+    const u32* ct = consts + (int)threadIdx.x * zero;
+    u32 pm[8], d2[8];
+    ld_elem(pm, ct);
+    ld_elem(d2, ct + 8);
+    TePoint acc;
+    te_identity<F>(acc);
+#pragma unroll 1
+    for (int j = 0; j < 8; j++) {
+        int g = chunk * 8 + j;
+        if (!((mask >> j) & 1) || g >= n_gens) continue;
+        u32 x[8], y[8], yp[8], ym[8], t2d[8];
+        ld_elem(x, gens_xy + 16 * (long)g);
+        ld_elem(y, gens_xy + 16 * (long)g + 8);
+        te_niels<F>(yp, ym, t2d, x, y, d2, pm);
+        te_madd<F>(acc, yp, ym, t2d, pm);
+    }
+    u32 zi[8], x[8], y[8], yp[8], ym[8], t2d[8];
+    fp_inv<F>(zi, acc.Z, pm);
+    fp_mul<F>(x, acc.X, zi, pm);
+    fp_mul<F>(y, acc.Y, zi, pm);
+    te_niels<F>(yp, ym, t2d, x, y, d2, pm);
+    u32* o = table + e * kEntryWords;
+    st_elem(o, yp);
+    st_elem(o + 8, ym);
+    st_elem(o + 16, t2d);
+}
+
+__device__ __forceinline__ void shfl_elem(u32* r, const u32* a, int src_lane) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = __shfl_sync(0xffffffffu, a[i], src_lane);
+}
+
+// 1/z for the 32 lanes of a warp with a single inversion: prefix and suffix product scans over the
+// warp, invert the total (every lane computes the same value -- free in SIMT), recombine.
+// All 32 lanes must call this; z must be non-zero (pass one for idle lanes).
+template <class F> __device__ __forceinline__ void warp_batch_inverse(u32* zinv, const u32* z, const u32* pm) {
+    const int lane = threadIdx.x & 31;
+    u32 pre[8], suf[8], t[8], m[8];
+    fp_copy(pre, z);
+    fp_copy(suf, z);
+#pragma unroll 1
+    for (int off = 1; off < 32; off <<= 1) {
+        int src = lane - off;
+        shfl_elem(t, pre, src < 0 ? lane : src);
+        fp_mul<F>(m, pre, t, pm);
+#pragma unroll
+        for (int i = 0; i < 8; i++) pre[i] = src >= 0 ? m[i] : pre[i];
+        src = lane + off;
+        shfl_elem(t, suf, src > 31 ? lane : src);
+        fp_mul<F>(m, suf, t, pm);
+#pragma unroll
+        for (int i = 0; i < 8; i++) suf[i] = src <= 31 ? m[i] : suf[i];
+    }
+    u32 total[8], inv[8], left[8], right[8], one[8];
+    shfl_elem(total, pre, 31);
+    fp_inv<F>(inv, total, pm);
+    fp_one<F>(one);
+    shfl_elem(left, pre, lane > 0 ? lane - 1 : lane);
+    shfl_elem(right, suf, lane < 31 ? lane + 1 : lane);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        left[i] = lane > 0 ? left[i] : one[i];
+        right[i] = lane < 31 ? right[i] : one[i];
+    }
+    fp_mul<F>(t, left, right, pm);
+    fp_mul<F>(zinv, t, inv, pm);
+}
+
+// 16 input bytes starting at `off` of a `len`-byte message (zero beyond len), as 4 LE words.
+__device__ __forceinline__ void load16(u32* w, const uint8_t* base, long off, long len) {
+    const uint8_t* p = base + off;
+    if (off + 16 <= len && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        uint4 v = *reinterpret_cast<const uint4*>(p);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        return;
+    }
+    w[0] = w[1] = w[2] = w[3] = 0;
+#pragma unroll 1
+    for (int k = 0; k < 16; k++) {
+        u32 b = (off + k < len) ? (u32)p[k] : 0u;
+        u32 sh = b << (8 * (k & 3));
+        w[0] |= (k >> 2) == 0 ? sh : 0u;
+        w[1] |= (k >> 2) == 1 ? sh : 0u;
+        w[2] |= (k >> 2) == 2 ? sh : 0u;
+        w[3] |= (k >> 2) == 3 ? sh : 0u;
+    }
+}
+
+// mode 0: out = n x (x, y); mode 1: out = n x x (TECompressor, R/crh/injective_map/mod.rs:24-31)
+template <class F>
+__global__ void __launch_bounds__(kPedBlock)
+k_pedersen_hash(PedersenDev P, const u32* __restrict__ consts, const u32* __restrict__ table,
+                const uint8_t* __restrict__ in, long len, long stride, const uint8_t* __restrict__ rand32,
+                u32* __restrict__ out, long n, int mode) {
+    extern __shared__ __align__(128) u32 sm[];          // 2 x kChunkWords
+    __shared__ __align__(8) unsigned long long full[2];
+    const int tid = threadIdx.x;
+    const int total = P.n_in_chunks + (rand32 ? P.n_rand_chunks : 0);
+    const unsigned full_s[2] = {(unsigned)__cvta_generic_to_shared(&full[0]), (unsigned)__cvta_generic_to_shared(&full[1])};
+    const unsigned buf_s[2] = {(unsigned)__cvta_generic_to_shared(sm), (unsigned)__cvta_generic_to_shared(sm + kChunkWords)};
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_s[0]));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_s[1]));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const u32* ct = consts + tid * P.zero;
+    u32 pm[8];
+    ld_elem(pm, ct);
+    unsigned uses0 = 0, uses1 = 0;                      // completed phases per buffer (CTA-uniform)
+
+    auto issue = [&](int chunk, int b) {                // thread 0 only
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_s[b]), "r"(kChunkBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf_s[b]),
+                     "l"(table + (long)chunk * kChunkWords), "r"(kChunkBytes), "r"(full_s[b])
+                     : "memory");
+    };
+
+    const long nblocks = (n + kPedBlock - 1) / kPedBlock;
+    for (long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const long i = blk * kPedBlock + tid;
+        const bool active = i < n;
+        const uint8_t* msg = in + (active ? i : 0) * stride;
+        const uint8_t* rnd = rand32 ? rand32 + (active ? i : 0) * 32 : nullptr;
+        TePoint acc;
+        te_identity<F>(acc);
+        if (tid == 0 && total > 0) {
+            issue(0, 0);
+            if (total > 1) issue(1, 1);
+        }
+        u32 w[4] = {0, 0, 0, 0};
+#pragma unroll 1
+        for (int c = 0; c < total; c++) {
+            const bool is_rand = c >= P.n_in_chunks;
+            const int bidx = is_rand ? c - P.n_in_chunks : c;
+            if ((bidx & 15) == 0) {
+                if (is_rand) load16(w, rnd, bidx, 32);
+                else load16(w, msg, bidx, len);
+            }
+            const int wi = (bidx >> 2) & 3;
+            u32 word = wi == 0 ? w[0] : wi == 1 ? w[1] : wi == 2 ? w[2] : w[3];
+            u32 byte = active ? (word >> (8 * (bidx & 3))) & 0xffu : 0u;
+            const int b = c & 1;
+            const unsigned parity = (b ? uses1 : uses0) & 1u;
+            unsigned done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done) : "r"(full_s[b]), "r"(parity) : "memory");
+            }
+            if (b) uses1++; else uses0++;
+            const u32* e = sm + b * kChunkWords + byte * kEntryWords;
+            u32 yp[8], ym[8], t2d[8];
+            ld_elem(yp, e);
+            ld_elem(ym, e + 8);
+            ld_elem(t2d, e + 16);
+            te_madd<F>(acc, yp, ym, t2d, pm);
+            __syncthreads();                            // every thread is done with buffer b
+            if (tid == 0 && c + 2 < total) issue(c + 2, b);
+        }
+        // projective -> affine (crh/pedersen/mod.rs:128 `result.into()`)
+        u32 z[8], zi[8], x[8], y[8];
+        if (active) fp_copy(z, acc.Z); else fp_one<F>(z);
+        warp_batch_inverse<F>(zi, z, pm);
+        if (active) {
+            fp_mul<F>(x, acc.X, zi, pm);
+            if (mode == 0) {
+                fp_mul<F>(y, acc.Y, zi, pm);
+                st_elem(out + 16 * i, x);
+                st_elem(out + 16 * i + 8, y);
+            } else {
+                st_elem(out + 8 * i, x);
+            }
+        }
+    }
+}
+
+// n x 2 child points (Montgomery x,y each) -> n x 128 bytes: canonical LE x_l || y_l || x_r || y_r
+template <class F>
+__global__ void k_points_to_bytes(const u32* __restrict__ children, u32* __restrict__ bytes_out, long n_elems) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_elems) return;
+    u32 a[8], one[8], pm[8];
+    ld_elem(a, children + 8 * i);
+    fp_zero(one);
+    one[0] = 1;
+    fp_modulus<F>(pm);
+    fp_mul<F>(a, a, one, pm);
+    st_elem(bytes_out + 8 * i, a);
+}
+
+}  // namespace cpb
+
+using namespace cpb;
+
+struct cpb_pedersen_ctx {
+    int curve_id = 0, field_id = 0, device = 0, sms = 148;
+    int window_size = 0, num_windows = 0, n_rand = 0;
+    size_t nbits = 0;
+    PedersenDev dev{};
+    u32* d_consts = nullptr;
+    u32* d_table = nullptr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    Scratch s_in, s_out, s_aux, s_rand;
+};
+
+extern "C" int cpb_poseidon_ctx_field(const cpb_poseidon_ctx* ctx);
+extern "C" int cpb_poseidon_ctx_device(const cpb_poseidon_ctx* ctx);
+
+namespace {
+
+struct CurveInfo {
+    int field_id;
+    bool d_is_ratio;      // d = -(num/den) when true, else d = num
+    uint64_t num, den;
+};
+bool curve_info(int curve_id, CurveInfo& ci) {
+    switch (curve_id) {
+        case CPB_JUBJUB: ci = {CPB_BLS12_381_FR, true, 10240, 10241}; return true;          // ark-ed-on-bls12-381: a=-1, d=-(10240/10241)
+        case CPB_ED_ON_BLS12_377: ci = {CPB_BLS12_377_FR, false, 3021, 1}; return true;     // ark-ed-on-bls12-377: a=-1, d=3021
+    }
+    return false;
+}
+
+template <class K> cpb_status ped_grid(K kernel, size_t smem, int sms, long n, int& grid) {
+    static thread_local const void* last = nullptr;
+    static thread_local int occ = 0;
+    if (last != (const void*)kernel) {
+        CPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kPedBlock, smem));
+        if (occ < 1) return fail(CPB_CUDA_ERROR, "pedersen kernel does not fit on an SM");
+        last = (const void*)kernel;
+    }
+    long need = (n + kPedBlock - 1) / kPedBlock, cap = (long)sms * occ;
+    grid = (int)(need < cap ? need : cap);
+    if (grid < 1) grid = 1;
+    return CPB_OK;
+}
+
+template <class F>
+cpb_status launch_hash_f(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, size_t stride, const uint8_t* rand32,
+                         u32* out, size_t n, int mode, cudaStream_t st) {
+    size_t smem = 2 * (size_t)kChunkBytes;
+    int grid = 1;
+    CPB_TRY(ped_grid(k_pedersen_hash<F>, smem, c->sms, (long)n, grid));
+    k_pedersen_hash<F><<<grid, kPedBlock, smem, st>>>(c->dev, c->d_consts, c->d_table, in, (long)len, (long)stride, rand32,
+                                                      out, (long)n, mode);
+    CPB_CUDA(cudaGetLastError());
+    return CPB_OK;
+}
+
+// length rules of the reference: R/crh/pedersen/mod.rs:82-89 (CRH) and R/commitment/pedersen/mod.rs:69-71
+cpb_status check_len(const cpb_pedersen_ctx* c, size_t len, bool commit) {
+    if (commit && len > c->nbits) return fail(CPB_BAD_LENGTH, "incorrect input length: %zu", len);
+    if (len * 8 > c->nbits)
+        return fail(CPB_BAD_LENGTH, "incorrect input length %zu for window params %dx%d", len, c->window_size, c->num_windows);
+    return CPB_OK;
+}
+
+cpb_status launch_hash(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, size_t stride, const uint8_t* rand32, u32* out,
+                       size_t n, int mode, cudaStream_t st) {
+    if (n == 0) return CPB_OK;
+    if (rand32 && c->n_rand == 0) return fail(CPB_BAD_PARAMS, "context has no randomness generators");
+    switch (c->field_id) {
+        case CPB_BLS12_381_FR: return launch_hash_f<Bls12_381_Fr>(c, in, len, stride, rand32, out, n, mode, st);
+        case CPB_BLS12_377_FR: return launch_hash_f<Bls12_377_Fr>(c, in, len, stride, rand32, out, n, mode, st);
+    }
+    return fail(CPB_UNSUPPORTED, "no kernel for base field %d", c->field_id);
+}
+
+cpb_status launch_points_to_bytes(cpb_pedersen_ctx* c, const u32* children, u32* bytes, size_t n_nodes, cudaStream_t st) {
+    long elems = (long)n_nodes * 4;
+    int grid = (int)((elems + 255) / 256);
+    switch (c->field_id) {
+        case CPB_BLS12_381_FR: k_points_to_bytes<Bls12_381_Fr><<<grid, 256, 0, st>>>(children, bytes, elems); break;
+        case CPB_BLS12_377_FR: k_points_to_bytes<Bls12_377_Fr><<<grid, 256, 0, st>>>(children, bytes, elems); break;
+        default: return fail(CPB_UNSUPPORTED, "no kernel for base field %d", c->field_id);
+    }
+    CPB_CUDA(cudaGetLastError());
+    return CPB_OK;
+}
+
+// TwoToOneCRH::evaluate buffer length, R/crh/pedersen/mod.rs:171: (HALF + HALF) / 8 with HALF = bits / 2
+size_t two_to_one_len(const cpb_pedersen_ctx* c) {
+    size_t half = c->nbits / 2, buf = (half + half) / 8;
+    return buf < 128 ? buf : 128;     // left||right of two 64-byte points; a longer buffer is zero padding
+}
+
+cpb_status two_to_one_dev(cpb_pedersen_ctx* c, const u32* children, u32* out, size_t n, u32* scratch_bytes, cudaStream_t st) {
+    if (n == 0) return CPB_OK;
+    CPB_TRY(check_len(c, two_to_one_len(c), false));
+    CPB_TRY(launch_points_to_bytes(c, children, scratch_bytes, n, st));
+    return launch_hash(c, (const uint8_t*)scratch_bytes, two_to_one_len(c), 128, nullptr, out, n, 0, st);
+}
+
+cpb_status ped_check(const cpb_pedersen_ctx* c) {
+    if (!c) return fail(CPB_NULL_POINTER, "null context");
+    return CPB_OK;
+}
+bool pow2_gt1(size_t n) { return n > 1 && (n & (n - 1)) == 0; }
+
+// heap-ordered inner levels of a byte tree (ByteDigestConverter + pedersen::TwoToOneCRH)
+cpb_status pedersen_levels(cpb_pedersen_ctx* node, const u32* leaf_xy, size_t n, u32* nodes_xy, u32* scratch_bytes,
+                           cudaStream_t st) {
+    size_t start = n / 2 - 1;
+    CPB_TRY(two_to_one_dev(node, leaf_xy, nodes_xy + 16 * start, n / 2, scratch_bytes, st));
+    while (start > 0) {
+        size_t upper = start;
+        start = (start - 1) / 2;
+        CPB_TRY(two_to_one_dev(node, nodes_xy + 16 * upper, nodes_xy + 16 * start, upper - start, scratch_bytes, st));
+    }
+    return CPB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+cpb_status cpb_pedersen_ctx_create(int curve_id, int window_size, int num_windows, const uint64_t* generators_xy,
+                                   size_t n_rand, const uint64_t* rand_generators_xy, int device, cpb_pedersen_ctx** out) {
+    if (!out) return fail(CPB_NULL_POINTER, "null out");
+    *out = nullptr;
+    CurveInfo ci;
+    if (!curve_info(curve_id, ci)) return fail(CPB_BAD_PARAMS, "unknown curve id %d", curve_id);
+    if (window_size < 1 || num_windows < 1 || (size_t)window_size * num_windows > (1u << 20))
+        return fail(CPB_BAD_PARAMS, "bad window %dx%d", window_size, num_windows);
+    if (!generators_xy || (n_rand && !rand_generators_xy)) return fail(CPB_NULL_POINTER, "null generators");
+    if (n_rand > 256) return fail(CPB_BAD_PARAMS, "at most 256 randomness generators");
+    host::Field F(host::field_modulus(ci.field_id));
+    host::Fe d = ci.d_is_ratio ? F.neg(F.mul(F.from_u64(ci.num), F.inv(F.from_u64(ci.den)))) : F.from_u64(ci.num);
+    host::Fe d2 = F.add(d, d);
+    const size_t nbits = (size_t)window_size * num_windows;
+    auto on_curve = [&](const uint64_t* xy) {
+        host::Fe x, y;
+        memcpy(x.l, xy, 32);
+        memcpy(y.l, xy + 4, 32);
+        if (!F.is_canonical(x) || !F.is_canonical(y)) return false;
+        host::Fe xx = F.mul(x, x), yy = F.mul(y, y);
+        return F.sub(yy, xx) == F.add(F.one(), F.mul(d, F.mul(xx, yy)));
+    };
+    for (size_t i = 0; i < nbits; i++)
+        if (!on_curve(generators_xy + 8 * i)) return fail(CPB_BAD_PARAMS, "generator %zu is not a reduced point on the curve", i);
+    for (size_t i = 0; i < n_rand; i++)
+        if (!on_curve(rand_generators_xy + 8 * i)) return fail(CPB_BAD_PARAMS, "randomness generator %zu is not on the curve", i);
+
+    DeviceGuard g(device);
+    if (!g.ok) { cudaGetLastError(); return fail(CPB_NO_DEVICE, "cudaSetDevice(%d) failed: no usable CUDA device", device); }
+    int major = 0;
+    CPB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return fail(CPB_NO_DEVICE, "device %d is sm_%d0; this library is built for sm_100a only", device, major);
+
+    cpb_pedersen_ctx* c = new cpb_pedersen_ctx();
+    c->curve_id = curve_id; c->field_id = ci.field_id; c->device = device; c->sms = sm_count(device);
+    c->window_size = window_size; c->num_windows = num_windows; c->n_rand = (int)n_rand; c->nbits = nbits;
+    c->dev.n_in_chunks = (int)(nbits / 8);
+    c->dev.n_rand_chunks = (int)((n_rand + 7) / 8);
+    c->dev.zero = 0;
+    const int total_chunks = c->dev.n_in_chunks + c->dev.n_rand_chunks;
+    uint64_t consts[12];
+    memcpy(consts, F.p, 32);
+    memcpy(consts + 4, d2.l, 32);
+    memcpy(consts + 8, d.l, 32);
+    u32 *d_gens = nullptr, *d_rgens = nullptr;
+    cudaError_t e = cudaMalloc(&c->d_consts, sizeof consts);
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_consts, consts, sizeof consts, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_table, (size_t)(total_chunks > 0 ? total_chunks : 1) * kChunkBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_gens, nbits * 64);
+    if (e == cudaSuccess) e = cudaMemcpy(d_gens, generators_xy, nbits * 64, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_rand) e = cudaMalloc(&d_rgens, n_rand * 64);
+    if (e == cudaSuccess && n_rand) e = cudaMemcpy(d_rgens, rand_generators_xy, n_rand * 64, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        auto build = [&](const u32* gens, int n_gens, int n_chunks, u32* table) {
+            if (n_chunks <= 0) return;
+            int grid = (n_chunks * 256 + 255) / 256;
+            // only the first floor(nbits/8)*8 input generators can ever be selected (see header)
+            if (c->field_id == CPB_BLS12_381_FR)
+                k_pedersen_table<Bls12_381_Fr><<<grid, 256>>>(c->d_consts, gens, n_gens, n_chunks, table, 0);
+            else
+                k_pedersen_table<Bls12_377_Fr><<<grid, 256>>>(c->d_consts, gens, n_gens, n_chunks, table, 0);
+        };
+        build(d_gens, (int)nbits, c->dev.n_in_chunks, c->d_table);
+        build(d_rgens, (int)n_rand, c->dev.n_rand_chunks, c->d_table + (size_t)c->dev.n_in_chunks * kChunkWords);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    if (d_gens) cudaFree(d_gens);
+    if (d_rgens) cudaFree(d_rgens);
+    if (e != cudaSuccess) {
+        if (c->d_consts) cudaFree(c->d_consts);
+        if (c->d_table) cudaFree(c->d_table);
+        if (c->stream) cudaStreamDestroy(c->stream);
+        delete c;
+        return fail(CPB_CUDA_ERROR, "pedersen context build failed: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return CPB_OK;
+}
+
+void cpb_pedersen_ctx_destroy(cpb_pedersen_ctx* c) {
+    if (!c) return;
+    DeviceGuard g(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->d_consts) cudaFree(c->d_consts);
+    if (c->d_table) cudaFree(c->d_table);
+    c->s_in.release(); c->s_out.release(); c->s_aux.release(); c->s_rand.release();
+    delete c;
+}
+
+// ---- device-pointer entry points
+cpb_status cpb_pedersen_crh_batch_dev(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, size_t stride, uint64_t* out_xy,
+                                      size_t n, void* stream) {
+    CPB_TRY(ped_check(c));
+    CPB_TRY(check_len(c, len, false));
+    DeviceGuard g(c->device);
+    return launch_hash(c, in, len, stride, nullptr, (u32*)out_xy, n, 0, (cudaStream_t)stream);
+}
+cpb_status cpb_pedersen_crh_x_batch_dev(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, size_t stride, uint64_t* out_x,
+                                        size_t n, void* stream) {
+    CPB_TRY(ped_check(c));
+    CPB_TRY(check_len(c, len, false));
+    DeviceGuard g(c->device);
+    return launch_hash(c, in, len, stride, nullptr, (u32*)out_x, n, 1, (cudaStream_t)stream);
+}
+cpb_status cpb_pedersen_commit_batch_dev(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, size_t stride,
+                                         const uint8_t* randomness_le32, uint64_t* out_xy, size_t n, void* stream) {
+    CPB_TRY(ped_check(c));
+    if (c->n_rand == 0) return fail(CPB_BAD_PARAMS, "context has no randomness generators");
+    if (!randomness_le32 && n) return fail(CPB_NULL_POINTER, "null randomness");
+    CPB_TRY(check_len(c, len, true));
+    DeviceGuard g(c->device);
+    return launch_hash(c, in, len, stride, randomness_le32, (u32*)out_xy, n, 0, (cudaStream_t)stream);
+}
+cpb_status cpb_pedersen_two_to_one_batch_dev(cpb_pedersen_ctx* c, const uint64_t* children_xy, uint64_t* out_xy, size_t n,
+                                             void* scratch_128n, void* stream) {
+    CPB_TRY(ped_check(c));
+    if (n && !scratch_128n) return fail(CPB_NULL_POINTER, "null scratch");
+    DeviceGuard g(c->device);
+    return two_to_one_dev(c, (const u32*)children_xy, (u32*)out_xy, n, (u32*)scratch_128n, (cudaStream_t)stream);
+}
+cpb_status cpb_merkle_pedersen_build_dev(cpb_pedersen_ctx* leaf, cpb_pedersen_ctx* node, const uint8_t* leaves,
+                                         size_t leaf_len, size_t leaf_stride, size_t n, uint64_t* leaf_nodes_xy,
+                                         uint64_t* non_leaf_nodes_xy, void* scratch_64n, void* stream) {
+    CPB_TRY(ped_check(leaf));
+    CPB_TRY(ped_check(node));
+    if (leaf->device != node->device || leaf->field_id != node->field_id)
+        return fail(CPB_BAD_PARAMS, "leaf and node contexts must share device and curve");
+    if (!pow2_gt1(n)) return fail(CPB_NOT_POW2, "leaves.len() should be power of two and greater than one (got %zu)", n);
+    if (!scratch_64n) return fail(CPB_NULL_POINTER, "null scratch");
+    CPB_TRY(check_len(leaf, leaf_len, false));
+    DeviceGuard g(leaf->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CPB_TRY(launch_hash(leaf, leaves, leaf_len, leaf_stride, nullptr, (u32*)leaf_nodes_xy, n, 0, st));
+    return pedersen_levels(node, (const u32*)leaf_nodes_xy, n, (u32*)non_leaf_nodes_xy, (u32*)scratch_64n, st);
+}
+cpb_status cpb_merkle_mixed_build_dev(cpb_pedersen_ctx* leaf, cpb_poseidon_ctx* node, const uint8_t* leaves, size_t leaf_len,
+                                      size_t leaf_stride, size_t n, uint64_t* leaf_nodes, uint64_t* non_leaf_nodes,
+                                      void* stream) {
+    CPB_TRY(ped_check(leaf));
+    if (!node) return fail(CPB_NULL_POINTER, "null context");
+    if (cpb_poseidon_ctx_field(node) != leaf->field_id || cpb_poseidon_ctx_device(node) != leaf->device)
+        return fail(CPB_BAD_PARAMS, "the Poseidon field must be the curve's base field, on the same device");
+    if (!pow2_gt1(n)) return fail(CPB_NOT_POW2, "leaves.len() should be power of two and greater than one (got %zu)", n);
+    CPB_TRY(check_len(leaf, leaf_len, false));
+    DeviceGuard g(leaf->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CPB_TRY(launch_hash(leaf, leaves, leaf_len, leaf_stride, nullptr, (u32*)leaf_nodes, n, 1, st));
+    return cpb_merkle_poseidon_from_digests_dev(node, leaf_nodes, n, non_leaf_nodes, stream);
+}
+
+// ---- host-pointer entry points
+static cpb_status ped_host_hash(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, size_t stride, const uint8_t* rnd,
+                                uint64_t* out, size_t n, int mode, bool commit) {
+    CPB_TRY(ped_check(c));
+    CPB_TRY(check_len(c, len, commit));
+    if (n == 0) return CPB_OK;
+    if ((!in && len) || !out) return fail(CPB_NULL_POINTER, "null buffer");
+    if (stride < len) return fail(CPB_BAD_PARAMS, "stride < len");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    size_t in_b = (n - 1) * stride + len, out_b = n * (mode == 0 ? 64 : 32);
+    CPB_TRY(c->s_in.reserve(in_b ? in_b : 16));
+    CPB_TRY(c->s_out.reserve(out_b));
+    if (in_b) CPB_CUDA(cudaMemcpyAsync(c->s_in.ptr, in, in_b, cudaMemcpyHostToDevice, c->stream));
+    const uint8_t* d_rnd = nullptr;
+    if (rnd) {
+        CPB_TRY(c->s_rand.reserve(n * 32));
+        CPB_CUDA(cudaMemcpyAsync(c->s_rand.ptr, rnd, n * 32, cudaMemcpyHostToDevice, c->stream));
+        d_rnd = (const uint8_t*)c->s_rand.ptr;
+    }
+    CPB_TRY(launch_hash(c, (const uint8_t*)c->s_in.ptr, len, stride, d_rnd, (u32*)c->s_out.ptr, n, mode, c->stream));
+    CPB_CUDA(cudaMemcpyAsync(out, c->s_out.ptr, out_b, cudaMemcpyDeviceToHost, c->stream));
+    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    return CPB_OK;
+}
+cpb_status cpb_pedersen_crh_batch(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, size_t stride, uint64_t* out_xy, size_t n) {
+    return ped_host_hash(c, in, len, stride, nullptr, out_xy, n, 0, false);
+}
+cpb_status cpb_pedersen_crh_x_batch(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, size_t stride, uint64_t* out_x, size_t n) {
+    return ped_host_hash(c, in, len, stride, nullptr, out_x, n, 1, false);
+}
+cpb_status cpb_pedersen_commit_batch(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, size_t stride,
+                                     const uint8_t* randomness_le32, uint64_t* out_xy, size_t n) {
+    CPB_TRY(ped_check(c));
+    if (c->n_rand == 0) return fail(CPB_BAD_PARAMS, "context has no randomness generators");
+    if (!randomness_le32 && n) return fail(CPB_NULL_POINTER, "null randomness");
+    return ped_host_hash(c, in, len, stride, randomness_le32, out_xy, n, 0, true);
+}
+cpb_status cpb_pedersen_two_to_one_batch(cpb_pedersen_ctx* c, const uint64_t* children_xy, uint64_t* out_xy, size_t n) {
+    CPB_TRY(ped_check(c));
+    if (n == 0) return CPB_OK;
+    if (!children_xy || !out_xy) return fail(CPB_NULL_POINTER, "null buffer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    CPB_TRY(c->s_in.reserve(n * 128));
+    CPB_TRY(c->s_aux.reserve(n * 128));
+    CPB_TRY(c->s_out.reserve(n * 64));
+    CPB_CUDA(cudaMemcpyAsync(c->s_in.ptr, children_xy, n * 128, cudaMemcpyHostToDevice, c->stream));
+    CPB_TRY(two_to_one_dev(c, (const u32*)c->s_in.ptr, (u32*)c->s_out.ptr, n, (u32*)c->s_aux.ptr, c->stream));
+    CPB_CUDA(cudaMemcpyAsync(out_xy, c->s_out.ptr, n * 64, cudaMemcpyDeviceToHost, c->stream));
+    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    return CPB_OK;
+}
+cpb_status cpb_merkle_pedersen_build(cpb_pedersen_ctx* leaf, cpb_pedersen_ctx* node, const uint8_t* leaves, size_t leaf_len,
+                                     size_t n, uint64_t* leaf_nodes_xy, uint64_t* non_leaf_nodes_xy) {
+    CPB_TRY(ped_check(leaf));
+    CPB_TRY(ped_check(node));
+    if (!pow2_gt1(n)) return fail(CPB_NOT_POW2, "leaves.len() should be power of two and greater than one (got %zu)", n);
+    if ((!leaves && leaf_len) || !leaf_nodes_xy || !non_leaf_nodes_xy) return fail(CPB_NULL_POINTER, "null buffer");
+    std::lock_guard<std::mutex> lk(leaf->mu);
+    DeviceGuard g(leaf->device);
+    CPB_TRY(leaf->s_in.reserve(n * leaf_len ? n * leaf_len : 16));
+    CPB_TRY(leaf->s_out.reserve(n * 64 + (n - 1) * 64));
+    CPB_TRY(leaf->s_aux.reserve(n * 64));
+    cudaStream_t st = leaf->stream;
+    u32* d_leaf = (u32*)leaf->s_out.ptr;
+    u32* d_nodes = d_leaf + 16 * n;
+    if (n * leaf_len) CPB_CUDA(cudaMemcpyAsync(leaf->s_in.ptr, leaves, n * leaf_len, cudaMemcpyHostToDevice, st));
+    CPB_TRY(cpb_merkle_pedersen_build_dev(leaf, node, (const uint8_t*)leaf->s_in.ptr, leaf_len, leaf_len, n, (uint64_t*)d_leaf,
+                                          (uint64_t*)d_nodes, leaf->s_aux.ptr, st));
+    CPB_CUDA(cudaMemcpyAsync(leaf_nodes_xy, d_leaf, n * 64, cudaMemcpyDeviceToHost, st));
+    CPB_CUDA(cudaMemcpyAsync(non_leaf_nodes_xy, d_nodes, (n - 1) * 64, cudaMemcpyDeviceToHost, st));
+    CPB_CUDA(cudaStreamSynchronize(st));
+    return CPB_OK;
+}
+cpb_status cpb_merkle_mixed_build(cpb_pedersen_ctx* leaf, cpb_poseidon_ctx* node, const uint8_t* leaves, size_t leaf_len,
+                                  size_t n, uint64_t* leaf_nodes, uint64_t* non_leaf_nodes) {
+    CPB_TRY(ped_check(leaf));
+    if (!node) return fail(CPB_NULL_POINTER, "null context");
+    if (!pow2_gt1(n)) return fail(CPB_NOT_POW2, "leaves.len() should be power of two and greater than one (got %zu)", n);
+    if ((!leaves && leaf_len) || !leaf_nodes || !non_leaf_nodes) return fail(CPB_NULL_POINTER, "null buffer");
+    std::lock_guard<std::mutex> lk(leaf->mu);
+    DeviceGuard g(leaf->device);
+    CPB_TRY(leaf->s_in.reserve(n * leaf_len ? n * leaf_len : 16));
+    CPB_TRY(leaf->s_out.reserve(n * 32 + (n - 1) * 32));
+    cudaStream_t st = leaf->stream;
+    u32* d_leaf = (u32*)leaf->s_out.ptr;
+    u32* d_nodes = d_leaf + 8 * n;
+    if (n * leaf_len) CPB_CUDA(cudaMemcpyAsync(leaf->s_in.ptr, leaves, n * leaf_len, cudaMemcpyHostToDevice, st));
+    CPB_TRY(cpb_merkle_mixed_build_dev(leaf, node, (const uint8_t*)leaf->s_in.ptr, leaf_len, leaf_len, n, (uint64_t*)d_leaf,
+                                       (uint64_t*)d_nodes, st));
+    CPB_CUDA(cudaMemcpyAsync(leaf_nodes, d_leaf, n * 32, cudaMemcpyDeviceToHost, st));
+    CPB_CUDA(cudaMemcpyAsync(non_leaf_nodes, d_nodes, (n - 1) * 32, cudaMemcpyDeviceToHost, st));
+    CPB_CUDA(cudaStreamSynchronize(st));
+    return CPB_OK;
+}
+
+}  // extern "C"

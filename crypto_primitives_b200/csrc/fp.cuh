@@ -72,6 +72,26 @@ template <class F> CPB_HD void fp_one(u32* r) {
 #pragma unroll
     for (int i = 0; i < 8; i++) r[i] = F::ONE(i);
 }
+// Load one element (32 B, 16-byte aligned) as two 128-bit accesses.
+CPB_HD void ld_elem(u32* r, const u32* p) {
+#if defined(__CUDA_ARCH__)
+    uint4 a = *reinterpret_cast<const uint4*>(p);
+    uint4 b = *reinterpret_cast<const uint4*>(p + 4);
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+    r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+#else
+    for (int i = 0; i < 8; i++) r[i] = p[i];
+#endif
+}
+CPB_HD void st_elem(u32* p, const u32* r) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4*>(p) = make_uint4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<uint4*>(p + 4) = make_uint4(r[4], r[5], r[6], r[7]);
+#else
+    for (int i = 0; i < 8; i++) p[i] = r[i];
+#endif
+}
+
 CPB_HD bool fp_eq(const u32* a, const u32* b) {
     u32 d = 0;
 #pragma unroll

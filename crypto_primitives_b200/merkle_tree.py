@@ -14,6 +14,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _native as N
+from .crh import pedersen as pedersen_crh
 from .crh import poseidon as poseidon_crh
 
 
@@ -70,6 +71,79 @@ class PoseidonFieldConfig(Config):
         non_leaf = np.empty((max(n - 1, 0), 4), dtype=np.uint64)
         N.check(N.lib.cpb_merkle_poseidon_from_digests(two_to_one_param.context(device), _p(d), n, _p(non_leaf)))
         return non_leaf
+
+
+class PedersenByteConfig(Config):
+    """Config{Leaf=[u8], LeafDigest=InnerDigest=C::Affine, ByteDigestConverter, LeafHash=pedersen::CRH,
+    TwoToOneHash=pedersen::TwoToOneCRH} -- JubJubMerkleTreeParams of R/merkle_tree/tests/mod.rs:19-33.
+    Digests are affine points, (2, 4) words."""
+
+    digest_words = 8
+
+    def leaf_hash_batch(self, leaf_param, leaves, device):
+        return pedersen_crh.CRH.evaluate_batch(leaf_param, leaves, device)
+
+    def two_to_one_batch(self, param, pairs, device):
+        return pedersen_crh.TwoToOneCRH.compress_batch(param, np.asarray(pairs).reshape(-1, 2, 2, 4), device)
+
+    def build(self, leaf_param, two_to_one_param, leaves, device):
+        lv = np.ascontiguousarray(leaves, dtype=np.uint8)
+        assert lv.ndim == 2, "leaves must be (n, leaf_len) bytes"
+        n, ln = lv.shape
+        leaf_nodes = np.empty((n, 2, 4), dtype=np.uint64)
+        non_leaf = np.empty((max(n - 1, 0), 2, 4), dtype=np.uint64)
+        try:
+            N.check(N.lib.cpb_merkle_pedersen_build(leaf_param.context(device), two_to_one_param.context(device),
+                                                    lv.ctypes.data_as(N.u8p), ln, n, _p(leaf_nodes), _p(non_leaf)))
+        except N.CpbError as e:
+            if e.status == N.CPB_BAD_LENGTH:
+                raise ValueError("incorrect input length") from e
+            raise
+        return leaf_nodes, non_leaf
+
+    def build_from_digests(self, two_to_one_param, leaf_digests, device):
+        d = np.ascontiguousarray(leaf_digests, dtype=np.uint64).reshape(-1, 2, 4)
+        n = d.shape[0]
+        if n < 2 or n & (n - 1):
+            raise ValueError("`leaves.len() should be power of two and greater than one")
+        nodes = np.empty((n - 1, 2, 4), dtype=np.uint64)
+        start = n // 2 - 1
+        nodes[start:] = self.two_to_one_batch(two_to_one_param, d.reshape(-1, 2, 2, 4), device)
+        while start > 0:
+            upper, start = start, (start - 1) // 2
+            nodes[start:upper] = self.two_to_one_batch(two_to_one_param, nodes[upper:2 * upper + 1].reshape(-1, 2, 2, 4), device)
+        return nodes
+
+    def default_leaf_digest(self):
+        raise NotImplementedError("Affine::default() (the identity) is not representable as an input digest here")
+
+
+class PedersenPoseidonConfig(Config):
+    """Config{Leaf=[u8], LeafHash=PedersenCRHCompressor<C,TECompressor,W>, LeafDigest=InnerDigest=Fq,
+    IdentityDigestConverter, TwoToOneHash=poseidon::TwoToOneCRH<Fq>} (BASELINE config 5)."""
+
+    def leaf_hash_batch(self, leaf_param, leaves, device):
+        return pedersen_crh.PedersenCRHCompressor.evaluate_batch(leaf_param, leaves, device)
+
+    def two_to_one_batch(self, param, pairs, device):
+        return poseidon_crh.TwoToOneCRH.compress_batch(param, pairs, device)
+
+    def build(self, leaf_param, two_to_one_param, leaves, device):
+        lv = np.ascontiguousarray(leaves, dtype=np.uint8)
+        n, ln = lv.shape
+        leaf_nodes = np.empty((n, 4), dtype=np.uint64)
+        non_leaf = np.empty((max(n - 1, 0), 4), dtype=np.uint64)
+        try:
+            N.check(N.lib.cpb_merkle_mixed_build(leaf_param.context(device), two_to_one_param.context(device),
+                                                 lv.ctypes.data_as(N.u8p), ln, n, _p(leaf_nodes), _p(non_leaf)))
+        except N.CpbError as e:
+            if e.status == N.CPB_BAD_LENGTH:
+                raise ValueError("incorrect input length") from e
+            raise
+        return leaf_nodes, non_leaf
+
+    def build_from_digests(self, two_to_one_param, leaf_digests, device):
+        return PoseidonFieldConfig().build_from_digests(two_to_one_param, leaf_digests, device)
 
 
 # ---- index helpers, mod.rs:728-786

@@ -56,7 +56,9 @@ typedef enum cpb_field {
 } cpb_field;
 
 typedef enum cpb_curve {
-    CPB_JUBJUB = 0        /* ark_ed_on_bls12_381::EdwardsProjective, base field = BLS12-381 Fr */
+    CPB_JUBJUB = 0,          /* ark_ed_on_bls12_381::EdwardsProjective (a=-1, d=-10240/10241), base field BLS12-381 Fr;
+                                the curve of R/merkle_tree/tests/mod.rs:8 and R/crh/pedersen/constraints.rs:168 */
+    CPB_ED_ON_BLS12_377 = 1  /* ark_ed_on_bls12_377 (a=-1, d=3021), base field BLS12-377 Fr; R/benches/crh.rs:5 */
 } cpb_curve;
 
 typedef struct cpb_poseidon_ctx cpb_poseidon_ctx;
@@ -96,6 +98,8 @@ cpb_status cpb_poseidon_ctx_create(int field_id, int rate, int capacity, int ful
 void cpb_poseidon_ctx_destroy(cpb_poseidon_ctx* ctx);
 /* 1 when the partial rounds run in sparse form, 0 for the dense fallback (same results). */
 int cpb_poseidon_ctx_is_sparse(const cpb_poseidon_ctx* ctx);
+int cpb_poseidon_ctx_field(const cpb_poseidon_ctx* ctx);
+int cpb_poseidon_ctx_device(const cpb_poseidon_ctx* ctx);
 
 /* n independent permutations of t-element states: PoseidonSponge::permute, mod.rs:98-121. */
 cpb_status cpb_poseidon_permute_batch(cpb_poseidon_ctx* ctx, const uint64_t* states_in, uint64_t* states_out, size_t n);
@@ -129,6 +133,68 @@ cpb_status cpb_merkle_poseidon_from_digests(cpb_poseidon_ctx* node_ctx, const ui
                                             uint64_t* non_leaf_nodes);
 cpb_status cpb_merkle_poseidon_from_digests_dev(cpb_poseidon_ctx* node_ctx, const uint64_t* leaf_digests, size_t n,
                                                 uint64_t* non_leaf_nodes, void* stream);
+
+/* ---- Pedersen CRH / commitment over a twisted-Edwards curve -------------------------------- */
+/* pedersen::Parameters{generators: Vec<Vec<C>>} (R/crh/pedersen/mod.rs:28-31) and, when n_rand > 0,
+ * commitment::pedersen::Parameters.randomness_generator (R/commitment/pedersen/mod.rs:17-21).
+ * generators_xy: num_windows x window_size affine points (x, y), generators[w][j] at index
+ * w*window_size + j; rand_generators_xy: n_rand points (the reference uses MODULUS_BIT_SIZE of the
+ * scalar field, :51-52), may be NULL when n_rand == 0.  The shim normalises the reference's
+ * projective points to affine before the call.  Points must be on the curve (else
+ * CPB_BAD_PARAMS); nothing else is assumed about them.  Builds the per-byte subset-sum tables on
+ * the GPU. */
+cpb_status cpb_pedersen_ctx_create(int curve_id, int window_size, int num_windows, const uint64_t* generators_xy,
+                                   size_t n_rand, const uint64_t* rand_generators_xy, int device,
+                                   cpb_pedersen_ctx** out);
+void cpb_pedersen_ctx_destroy(cpb_pedersen_ctx* ctx);
+
+/* n x pedersen::CRH::evaluate (R/crh/pedersen/mod.rs:76-129): input i is the `len` bytes at
+ * in + i*stride, zero-padded by the callee to WINDOW_SIZE*NUM_WINDOWS/8 bytes (:94-99); bit k of
+ * byte b selects generator 8b+k (:200-209).  len*8 > WINDOW_SIZE*NUM_WINDOWS -> CPB_BAD_LENGTH
+ * (the reference panics, :82-89).  out_xy: n affine points. */
+cpb_status cpb_pedersen_crh_batch(cpb_pedersen_ctx* ctx, const uint8_t* in, size_t len, size_t stride,
+                                  uint64_t* out_xy, size_t n);
+cpb_status cpb_pedersen_crh_batch_dev(cpb_pedersen_ctx* ctx, const uint8_t* in, size_t len, size_t stride,
+                                      uint64_t* out_xy, size_t n, void* stream);
+/* n x PedersenCRHCompressor<C, TECompressor, W>::evaluate (R/crh/injective_map/mod.rs:22-62): the
+ * x-coordinate of the CRH output, one base-field element each. */
+cpb_status cpb_pedersen_crh_x_batch(cpb_pedersen_ctx* ctx, const uint8_t* in, size_t len, size_t stride,
+                                    uint64_t* out_x, size_t n);
+cpb_status cpb_pedersen_crh_x_batch_dev(cpb_pedersen_ctx* ctx, const uint8_t* in, size_t len, size_t stride,
+                                        uint64_t* out_x, size_t n, void* stream);
+/* n x pedersen::TwoToOneCRH::compress (R/crh/pedersen/mod.rs:187-197): children_xy = n x (left, right)
+ * affine points, each serialised uncompressed (x || y, 32-byte LE canonical; R/macros.rs:3-13) and
+ * hashed as in `evaluate` (:152-182).  The _dev form needs 128*n bytes of device scratch. */
+cpb_status cpb_pedersen_two_to_one_batch(cpb_pedersen_ctx* ctx, const uint64_t* children_xy, uint64_t* out_xy, size_t n);
+cpb_status cpb_pedersen_two_to_one_batch_dev(cpb_pedersen_ctx* ctx, const uint64_t* children_xy, uint64_t* out_xy,
+                                             size_t n, void* scratch_128n, void* stream);
+/* n x CommitmentScheme::commit (R/commitment/pedersen/mod.rs:62-105): CRH of the padded input plus
+ * sum_k bit_k(r) * randomness_generator[k]; randomness_le32 = n x 32-byte little-endian canonical
+ * scalars (`randomness.0.into_bigint()`, :93).  len > WINDOW_SIZE*NUM_WINDOWS (the reference's own
+ * guard compares bytes with bits, :69) or len*8 > WINDOW_SIZE*NUM_WINDOWS -> CPB_BAD_LENGTH. */
+cpb_status cpb_pedersen_commit_batch(cpb_pedersen_ctx* ctx, const uint8_t* in, size_t len, size_t stride,
+                                     const uint8_t* randomness_le32, uint64_t* out_xy, size_t n);
+cpb_status cpb_pedersen_commit_batch_dev(cpb_pedersen_ctx* ctx, const uint8_t* in, size_t len, size_t stride,
+                                         const uint8_t* randomness_le32, uint64_t* out_xy, size_t n, void* stream);
+
+/* ---- Merkle tree, byte leaves -------------------------------------------------------------- */
+/* MerkleTree::new for Config{Leaf=[u8], LeafHash=pedersen::CRH, LeafInnerDigestConverter=
+ * ByteDigestConverter, TwoToOneHash=pedersen::TwoToOneCRH} -- JubJubMerkleTreeParams of
+ * R/merkle_tree/tests/mod.rs:19-33.  Digests are affine points (8 words).  The _dev form needs
+ * 64*n bytes of device scratch. */
+cpb_status cpb_merkle_pedersen_build(cpb_pedersen_ctx* leaf_ctx, cpb_pedersen_ctx* node_ctx, const uint8_t* leaves,
+                                     size_t leaf_len, size_t n, uint64_t* leaf_nodes_xy, uint64_t* non_leaf_nodes_xy);
+cpb_status cpb_merkle_pedersen_build_dev(cpb_pedersen_ctx* leaf_ctx, cpb_pedersen_ctx* node_ctx, const uint8_t* leaves,
+                                         size_t leaf_len, size_t leaf_stride, size_t n, uint64_t* leaf_nodes_xy,
+                                         uint64_t* non_leaf_nodes_xy, void* scratch_64n, void* stream);
+/* MerkleTree::new for Config{Leaf=[u8], LeafHash=PedersenCRHCompressor<C,TECompressor,W>,
+ * IdentityDigestConverter, TwoToOneHash=poseidon::TwoToOneCRH<Fq>} (BASELINE config 5): leaf digest =
+ * x-coordinate, a base-field element; the Poseidon field must be the curve's base field. */
+cpb_status cpb_merkle_mixed_build(cpb_pedersen_ctx* leaf_ctx, cpb_poseidon_ctx* node_ctx, const uint8_t* leaves,
+                                  size_t leaf_len, size_t n, uint64_t* leaf_nodes, uint64_t* non_leaf_nodes);
+cpb_status cpb_merkle_mixed_build_dev(cpb_pedersen_ctx* leaf_ctx, cpb_poseidon_ctx* node_ctx, const uint8_t* leaves,
+                                      size_t leaf_len, size_t leaf_stride, size_t n, uint64_t* leaf_nodes,
+                                      uint64_t* non_leaf_nodes, void* stream);
 
 #ifdef __cplusplus
 }

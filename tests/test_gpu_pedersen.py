@@ -1,0 +1,171 @@
+"""GPU parity tests for Pedersen CRH / two-to-one / commitment and the byte-leaf and mixed Merkle
+builds, through the C-ABI, against the oracle -- bit-exact.  PARITY UNPINNED w.r.t. the reference
+(no golden vectors exist for this path); pinned to the oracle, whose curve arithmetic is checked
+independently in tests/test_oracle_pedersen.py."""
+import numpy as np
+import pytest
+
+from helpers import oracle_config, product_config
+import crypto_primitives_b200 as cp
+from crypto_primitives_b200 import _native as N
+from crypto_primitives_b200.commitment.pedersen import Commitment, randomness_bytes
+from crypto_primitives_b200.crh.pedersen import CRH, Parameters, PedersenCRHCompressor, TwoToOneCRH, Window
+from crypto_primitives_b200.merkle_tree import MerkleTree, PedersenByteConfig, PedersenPoseidonConfig
+from oracle import cref, fields as OF, jubjub as jj, pedersen as OPD
+
+pytestmark = pytest.mark.gpu
+
+_cache = {}
+
+
+def setup(ws, nw, seed, commitment=False):
+    key = (ws, nw, seed, commitment)
+    if key not in _cache:
+        ow = OPD.Window(ws, nw)
+        oprm = OPD.setup(ow, seed, commitment)
+        f = cp.BLS12_381_FR
+        g = f.elements([c for w in oprm.generators for pt in w for c in pt]).reshape(nw, ws, 2, 4)
+        r = f.elements([c for pt in oprm.randomness_generator for c in pt]).reshape(-1, 2, 4) if commitment else None
+        _cache[key] = (ow, oprm, cref.Pedersen(oprm, ow), Parameters(cp.curves.JUBJUB, Window(ws, nw), g, r))
+    return _cache[key]
+
+
+@pytest.mark.parametrize("ws,nw,lens", [(4, 256, (128, 32, 0, 1, 77)),     # R/merkle_tree/tests/mod.rs:12-17
+                                        (127, 9, (142, 128)),              # R/crh/pedersen/constraints.rs:174-177 (1143 bits)
+                                        (4, 9, (4, 2)),                    # R/commitment/pedersen/constraints.rs:164-167
+                                        (250, 8, (128, 250))])             # R/benches/crh.rs:14-17
+def test_crh_matches_oracle(ws, nw, lens):
+    ow, oprm, oc, prm = setup(ws, nw, 5)
+    for ln in lens:
+        n = 300
+        inp = cref.synth_bytes(100 + ln, n * max(ln, 1)).reshape(n, max(ln, 1))[:, :ln]
+        inp = np.ascontiguousarray(inp)
+        if ln:
+            inp[0, :] = 0xFF
+            inp[1, :] = 0
+        exp = oc.batch(inp, threads=8)
+        got = CRH.evaluate_batch(prm, inp)
+        assert np.array_equal(got, exp), (ws, nw, ln)
+        assert np.array_equal(PedersenCRHCompressor.evaluate_batch(prm, inp), exp[:, 0])     # TECompressor = x
+    # python big-int oracle on one input (ties C oracle, Python oracle and GPU together)
+    one = bytes(inp[5])
+    assert tuple(cp.BLS12_381_FR.to_ints(CRH.evaluate(prm, one))) == OPD.crh_evaluate(oprm, ow, one)
+
+
+def test_input_too_long_is_rejected():
+    """R/crh/pedersen/mod.rs:82-89 panics; the ABI returns CPB_BAD_LENGTH."""
+    _, _, _, prm = setup(4, 9, 5)
+    with pytest.raises(ValueError):
+        CRH.evaluate_batch(prm, np.zeros((2, 5), dtype=np.uint8))          # 40 bits > 36
+    out = np.zeros((1, 2, 4), dtype=np.uint64)
+    st = N.lib.cpb_pedersen_crh_batch(prm.context(0), np.zeros(8, dtype=np.uint8).ctypes.data_as(N.u8p), 5, 5,
+                                      out.ctypes.data_as(N.u64p), 1)
+    assert st == N.CPB_BAD_LENGTH
+
+
+def test_generators_off_curve_are_rejected():
+    _, _, _, prm = setup(4, 9, 5)
+    bad = prm.generators.copy()
+    bad[0, 0, 0, 0] ^= np.uint64(1)
+    with pytest.raises(N.CpbError) as e:
+        Parameters(prm.curve, prm.window, bad).context(0)
+    assert e.value.status == N.CPB_BAD_PARAMS
+
+
+def test_two_to_one_matches_oracle():
+    ow, oprm, oc, prm = setup(4, 256, 5)
+    pts = oc.batch(cref.synth_bytes(7, 64 * 128).reshape(64, 128), threads=8)       # 64 valid points
+    kids = pts.reshape(32, 2, 2, 4)
+    exp = oc.compress_batch(kids, threads=8)
+    assert np.array_equal(TwoToOneCRH.compress_batch(prm, kids), exp)
+    assert np.array_equal(TwoToOneCRH.compress(prm, kids[3, 0], kids[3, 1]), exp[3])
+    # evaluate on raw bytes == CRH on the concatenation (R/crh/pedersen/mod.rs:152-182)
+    l, r = bytes(range(64)), bytes(range(64, 128))
+    assert np.array_equal(TwoToOneCRH.evaluate(prm, l, r), CRH.evaluate(prm, l + r))
+
+
+@pytest.mark.parametrize("ws,nw,ln", [(4, 256, 128), (4, 256, 50), (4, 9, 4)])
+def test_commitment_matches_oracle(ws, nw, ln):
+    ow, oprm, oc, prm = setup(ws, nw, 9, commitment=True)
+    n = 200
+    inp = np.ascontiguousarray(cref.synth_bytes(31, n * ln).reshape(n, ln))
+    rs = [OF.SplitMix64(500 + i).field(OF.JUBJUB_FR) for i in range(n)]
+    rs[0], rs[1], rs[2] = 0, 1, OF.JUBJUB_FR - 1
+    rb = randomness_bytes(cp.curves.JUBJUB, rs)
+    exp = oc.batch(inp, rb, threads=8)
+    assert np.array_equal(Commitment.commit_batch(prm, inp, rb), exp)
+    assert np.array_equal(Commitment.commit(prm, bytes(inp[7]), rs[7]), exp[7])
+    # commit with r = 0 is the plain CRH of the padded input
+    assert np.array_equal(exp[0], CRH.evaluate_batch(prm, inp[:1])[0])
+    with pytest.raises(ValueError):
+        Commitment.commit_batch(prm, np.zeros((1, ws * nw // 8 + 1), dtype=np.uint8), rb[:1])
+
+
+def test_linearity_property_large_batch():
+    """Size-independent property at BASELINE config 3 scale (2^20 x 128 B is replayed by the oracle only
+    on a sample): H(a) + H(b) == H(a|b) when a and b have disjoint bits -- checked with the oracle's
+    group law on sampled rows, plus determinism of the whole batch."""
+    ow, oprm, oc, prm = setup(4, 256, 5)
+    n = 1 << 16
+    a = cref.synth_bytes(1, n * 128).reshape(n, 128) & np.uint8(0x0F)
+    b = cref.synth_bytes(2, n * 128).reshape(n, 128) & np.uint8(0xF0)
+    ha, hb, hab = (CRH.evaluate_batch(prm, x) for x in (a, b, a | b))
+    assert np.array_equal(hab, CRH.evaluate_batch(prm, a | b))
+    f = cp.BLS12_381_FR
+    for i in (0, 1, 1000, n - 1):
+        pa, pb, pab = (tuple(f.to_ints(h[i])) for h in (ha, hb, hab))
+        assert jj.add(pa, pb) == pab and jj.is_on_curve(pab)
+    idx = np.random.default_rng(0).choice(n, 256, replace=False)
+    assert np.array_equal(hab[idx], oc.batch(np.ascontiguousarray((a | b)[idx]), threads=8))
+
+
+def test_pedersen_merkle_tree_reference_scenario():
+    """bytes_mt_tests::good_root_test (R/merkle_tree/tests/mod.rs:94-131): 2, 4 and 128 leaves of 32 bytes
+    (BigInteger256 serialised), window 4x256, proofs / multiproof / updates."""
+    ow, oprm, oc, prm = setup(4, 256, 5)
+    cfg = PedersenByteConfig()
+    for n, updates in ((2, (0, 1)), (4, (3,)), (128, (2, 3, 5, 111, 127))):
+        leaves = np.ascontiguousarray(cref.synth_bytes(60 + n, n * 32).reshape(n, 32))
+        tree = MerkleTree.new(prm, prm, leaves, config=cfg)
+        exp_leaf, exp_nodes = cref.pedersen_merkle(oc, oc, leaves, threads=8)
+        assert np.array_equal(tree.leaf_nodes, exp_leaf) and np.array_equal(tree.non_leaf_nodes, exp_nodes)
+        root = tree.root()
+        for i in {0, n - 1, n // 2}:
+            assert tree.generate_proof(i).verify(prm, prm, root, leaves[i], config=cfg)
+        if n <= 4:
+            assert tree.generate_multi_proof(range(n)).verify(prm, prm, root, leaves, config=cfg)
+        new = cref.synth_bytes(70 + n, len(updates) * 32).reshape(len(updates), 32)
+        for k, i in enumerate(updates):
+            tree.update(i, new[k])
+            leaves[i] = new[k]
+        exp_leaf, exp_nodes = cref.pedersen_merkle(oc, oc, leaves, threads=8)
+        assert np.array_equal(tree.non_leaf_nodes, exp_nodes)
+        assert tree.generate_proof(updates[-1]).verify(prm, prm, tree.root(), leaves[updates[-1]], config=cfg)
+
+
+def test_mixed_tree_matches_oracle():
+    """BASELINE config 5 shape: Pedersen leaf hash (x-coordinate) + Poseidon two-to-one over BLS12-381 Fr."""
+    ow, oprm, oc, prm = setup(4, 256, 5)
+    _, ocfg = oracle_config("bls_default_r2")
+    pcfg = product_config("bls_default_r2")
+    n = 512
+    leaves = np.ascontiguousarray(cref.synth_bytes(88, n * 128).reshape(n, 128))
+    exp_leaf, exp_nodes = cref.mixed_merkle(oc, cref.Poseidon(ocfg), leaves, threads=8)
+    tree = MerkleTree.new(prm, pcfg, leaves, config=PedersenPoseidonConfig())
+    assert np.array_equal(tree.leaf_nodes, exp_leaf) and np.array_equal(tree.non_leaf_nodes, exp_nodes)
+    assert tree.generate_proof(77).verify(prm, pcfg, tree.root(), leaves[77], config=PedersenPoseidonConfig())
+
+
+def test_ed_on_bls12_377_curve_smoke():
+    """Second curve id (the curve of R/benches/crh.rs): generators made by the mirror's own setup; outputs
+    must be on the curve, linear in the input bits and independent of batch position."""
+    curve = cp.curves.ED_ON_BLS12_377
+    w = Window(8, 16)
+    prm = CRH.setup(OF.SplitMix64(42), w, curve)
+    f = curve.base_field
+    a = np.zeros((3, 16), dtype=np.uint8)
+    a[0, 0], a[1, 0], a[2, 0] = 0x05, 0x50, 0x55
+    h = [tuple(f.to_ints(x)) for x in CRH.evaluate_batch(prm, a)]
+    assert all(curve.is_on_curve(p) for p in h) and curve.add(h[0], h[1]) == h[2]
+    g00 = tuple(f.to_ints(prm.generators[0, 0]))
+    assert h[0] == curve.mul(5, g00)                       # generators[0][j] = 2^j * G_0 (R/crh/pedersen/mod.rs:48-56)
