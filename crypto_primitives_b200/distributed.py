@@ -1,0 +1,145 @@
+"""Leaf-sharded Merkle build across the GPUs of one node.
+
+The reference has no distributed path: MerkleTree::new (R/merkle_tree/mod.rs:411-523) runs in one
+process with one rayon barrier per level.  A height-h tree over N leaves on G = 2^g ranks is G
+independent subtrees over contiguous leaf ranges plus a g-level top, so:
+
+  1. rank k hashes leaves [k*N/G, (k+1)*N/G) and builds its whole local subtree on its own GPU
+     (no communication);
+  2. ONE all-gather of the G subtree roots (32 B each) over NCCL / NVLink;
+  3. every rank computes the top g levels (G-1 hashes) redundantly -- cheaper than a second collective.
+
+`gather="levels"` additionally all-gathers every level (and the leaf digests) so that each rank
+holds the reference's complete `leaf_nodes` / `non_leaf_nodes` arrays: because the node array is
+heap-ordered by level, rank k's nodes of global level l >= g are the k-th contiguous slice of
+that level, so each level is one in-place all_gather_into_tensor -- no repacking.
+
+One process per GPU (torchrun); torch.distributed is plumbing only.  The hashing backend is
+injected so the sharding / collective logic can be exercised on CPU with gloo (tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+def _log2(n: int) -> int:
+    assert n > 0 and n & (n - 1) == 0, "must be a power of two"
+    return n.bit_length() - 1
+
+
+class CudaPoseidonBackend:
+    """Field-leaf tree: poseidon::CRH leaves + poseidon::TwoToOneCRH nodes on the current CUDA device."""
+
+    digest_words = 4
+
+    def __init__(self, leaf_params, node_params, device_index: int):
+        from . import _native as N
+        self.N = N
+        self.dev = device_index
+        self.leaf_ctx = leaf_params.context(device_index)
+        self.node_ctx = node_params.context(device_index)
+
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def build_local(self, leaves: torch.Tensor):
+        """leaves (n, L, 4) int64 on the GPU -> (leaf_nodes (n,4), nodes (n-1,4)) heap order."""
+        n, L = leaves.shape[0], leaves.shape[1]
+        leaf_nodes = torch.empty((n, 4), dtype=torch.int64, device=leaves.device)
+        nodes = torch.empty((n - 1, 4), dtype=torch.int64, device=leaves.device)
+        self.N.check(self.N.lib.cpb_merkle_poseidon_build_dev(self.leaf_ctx, self.node_ctx, leaves.data_ptr(), L, n,
+                                                              leaf_nodes.data_ptr(), nodes.data_ptr(), self._stream()))
+        return leaf_nodes, nodes
+
+    def hash_leaves(self, leaves: torch.Tensor):
+        n, L = leaves.shape[0], leaves.shape[1]
+        out = torch.empty((n, 4), dtype=torch.int64, device=leaves.device)
+        self.N.check(self.N.lib.cpb_poseidon_crh_batch_dev(self.leaf_ctx, leaves.data_ptr(), L, out.data_ptr(), n, self._stream()))
+        return out
+
+    def from_digests(self, digests: torch.Tensor):
+        """digests (m, 4), m a power of two >= 2 -> (m-1, 4) heap-ordered inner nodes."""
+        m = digests.shape[0]
+        nodes = torch.empty((m - 1, 4), dtype=torch.int64, device=digests.device)
+        self.N.check(self.N.lib.cpb_merkle_poseidon_from_digests_dev(self.node_ctx, digests.data_ptr(), m, nodes.data_ptr(),
+                                                                     self._stream()))
+        return nodes
+
+
+@dataclass
+class ShardedTree:
+    """Result of a sharded build on this rank."""
+    root: torch.Tensor                    # (digest_words,)
+    n_leaves: int                         # global
+    world: int
+    rank: int
+    local_leaf_nodes: torch.Tensor        # this rank's leaf digests (n/G, w)
+    local_nodes: torch.Tensor | None      # this rank's subtree inner nodes, heap order (n/G - 1, w); None when n/G == 1
+    top_nodes: torch.Tensor | None        # the replicated top g levels, heap order (G - 1, w); None when G == 1
+    leaf_nodes: torch.Tensor | None = None       # gather="levels": the reference's full arrays on every rank
+    non_leaf_nodes: torch.Tensor | None = None
+
+    def height(self) -> int:
+        return _log2(self.n_leaves) + 1
+
+
+def level_slices(n_leaves: int, world: int, rank: int):
+    """For every global inner level l in [g, log2 n): (global_start, count_per_rank, local_start) describing
+    where rank's nodes of that level live in the global and in the local heap-ordered arrays."""
+    g, h = _log2(world), _log2(n_leaves)
+    out = []
+    for l in range(g, h):
+        width = 1 << l                     # nodes at global level l
+        per = width // world
+        out.append(((1 << l) - 1 + rank * per, per, (1 << (l - g)) - 1))
+    return out
+
+
+def sharded_merkle_build(backend, local_leaves: torch.Tensor, gather: str = "roots", group=None) -> ShardedTree:
+    """Build the tree whose leaves are the concatenation over ranks of `local_leaves` (rank order)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    g = _log2(world)
+    n_local = local_leaves.shape[0]
+    _log2(n_local)
+    n = n_local * world
+    if n < 2:
+        raise ValueError("`leaves.len() should be power of two and greater than one")
+    w = backend.digest_words
+
+    if n_local >= 2:
+        leaf_nodes, nodes = backend.build_local(local_leaves)
+        local_root = nodes[0]
+    else:
+        leaf_nodes, nodes = backend.hash_leaves(local_leaves), None
+        local_root = leaf_nodes[0]
+
+    top = None
+    if world > 1:
+        roots = torch.empty((world, w), dtype=local_root.dtype, device=local_root.device)
+        dist.all_gather_into_tensor(roots, local_root.reshape(1, w).contiguous(), group=group)   # the one collective
+        top = backend.from_digests(roots)
+        root = top[0]
+    else:
+        root = local_root
+
+    tree = ShardedTree(root, n, world, rank, leaf_nodes, nodes, top)
+    if gather == "levels":
+        full_leaf = torch.empty((n, w), dtype=leaf_nodes.dtype, device=leaf_nodes.device)
+        full_nodes = torch.empty((n - 1, w), dtype=leaf_nodes.dtype, device=leaf_nodes.device)
+        if world > 1:
+            dist.all_gather_into_tensor(full_leaf, leaf_nodes.contiguous(), group=group)
+            full_nodes[: world - 1] = top
+            for gstart, per, lstart in level_slices(n, world, rank):
+                seg = full_nodes[gstart - rank * per: gstart - rank * per + per * world]
+                dist.all_gather_into_tensor(seg, nodes[lstart: lstart + per].contiguous(), group=group)
+        else:
+            full_leaf.copy_(leaf_nodes)
+            full_nodes.copy_(nodes)
+        tree.leaf_nodes, tree.non_leaf_nodes = full_leaf, full_nodes
+    elif gather != "roots":
+        raise ValueError("gather must be 'roots' or 'levels'")
+    return tree
