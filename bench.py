@@ -221,7 +221,7 @@ def run_b200(args):
         e1.record()
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
-        root = tree.root
+        root = tree.root.clone()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([sum(times)], dtype=torch.float64, device=dev)

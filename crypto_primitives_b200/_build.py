@@ -13,7 +13,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
-LIB = os.path.join(HERE, "libcpb200.so")
+LIB = os.path.join(HERE, os.environ.get("CPB_LIB_NAME", "libcpb200.so"))
+EXTRA = os.environ.get("CPB_NVCC_EXTRA", "").split()
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC",]
@@ -46,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJ, src[:-3] + ".o")
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= dep_t:
             return obj
-        cmd = [NVCC, *FLAGS, "-Xptxas", "-v", "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *FLAGS, *EXTRA, "-Xptxas", "-v", "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcpb200.so")
+LIB_PATH = os.path.join(HERE, os.environ.get("CPB_LIB_NAME", "libcpb200.so"))   # CPB_LIB_NAME: development variants only
 
 u64p = C.POINTER(C.c_uint64)
 u8p = C.POINTER(C.c_uint8)

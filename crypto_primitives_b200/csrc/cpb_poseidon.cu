@@ -47,9 +47,12 @@ int sm_count(int device) {
 
 // ------------------------------------------------------------------------------ kernels
 constexpr int kBlock = 128;
+#ifndef CPB_POS_MINBLOCKS
+#define CPB_POS_MINBLOCKS 5
+#endif
 
 template <class F, int T>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, CPB_POS_MINBLOCKS)
 k_poseidon_crh(PoseidonDev P, const u32* __restrict__ consts, const u32* __restrict__ in, u32* __restrict__ out,
                long n, long len) {
     extern __shared__ __align__(16) u32 cs[];
@@ -67,7 +70,7 @@ k_poseidon_crh(PoseidonDev P, const u32* __restrict__ consts, const u32* __restr
 }
 
 template <class F, int T>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, CPB_POS_MINBLOCKS)
 k_poseidon_permute(PoseidonDev P, const u32* __restrict__ consts, const u32* __restrict__ in, u32* __restrict__ out,
                    long n) {
     extern __shared__ __align__(16) u32 cs[];

@@ -47,14 +47,13 @@ template <int T> CPB_HD void pos_rotl(u32 (&s)[T][8]) {
 // this is k squarings and one multiplication -- the optimal chain -- from a single pair of
 // inlined multiplier bodies, which keeps the kernel's instruction footprint small.
 template <class F> CPB_HD void pos_sbox(u32* x, u64 alpha, int top_bit, const u32* pm) {
-    u32 t[8];
-    fp_copy(t, x);
+    u32 x0[8];
+    fp_copy(x0, x);
 #pragma unroll 1
     for (int i = top_bit - 1; i >= 0; i--) {
-        fp_sqr<F>(t, t, pm);
-        if ((alpha >> i) & 1) fp_mul<F>(t, t, x, pm);
+        fp_sqr<F>(x, x, pm);
+        if ((alpha >> i) & 1) fp_mul<F>(x, x, x0, pm);
     }
-    fp_copy(x, t);
 }
 
 // The permutation, one rolled loop over all RF+RP rounds with a single instance of each
@@ -93,31 +92,38 @@ template <class F, int T> CPB_HD void pos_permute(u32 (&s)[T][8], const Poseidon
         const u32* rows = dense ? cs + 8 * ((full && r == half - 1) ? P.off_mpre : P.off_m)
                                 : cs + 8 * (P.off_sp + k * (2 * T - 1));
         const int nrows = dense ? T : 1;
-        u32 n[T][8];
+        u32 n[T][8], d[8];
 #pragma unroll 1
         for (int i = 0; i < nrows; i++) {
-            u32 d[8];
             fp_dot<F, T>(d, s, rows + 8 * T * i, pm);
-            // shift d in at the end: after nrows == T iterations n[i] holds row i
+            if (dense) {                        // collect row i; after T iterations n[i] holds row i
 #pragma unroll
-            for (int q = 0; q + 1 < T; q++) fp_copy(n[q], n[q + 1]);
-            fp_copy(n[T - 1], d);
+                for (int q = 0; q + 1 < T; q++) fp_copy(n[q], n[q + 1]);
+                fp_copy(n[T - 1], d);
+            }
         }
         if (dense) {
 #pragma unroll
             for (int i = 0; i < T; i++) fp_copy(s[i], n[i]);
         } else {
-            // s_j += v_j * s_0 for j >= 1 (old s_0), then s_0 <- row product (+ next lane-0 constant)
+            // s_j += v_j * s_0 for j >= 1 (old s_0), then s_0 <- row product d (+ next lane-0 constant)
             const u32* v = rows + 8 * T;
-            if (T > 1) {
+            if (T <= 4) {
+#pragma unroll
+                for (int j = 1; j < T; j++) {
+                    u32 c[8], tmp[8];
+                    ld_elem(c, v + 8 * (j - 1));
+                    fp_mul<F>(tmp, s[0], c, pm);
+                    fp_add<F>(s[j], s[j], tmp);
+                }
+            } else {
 #pragma unroll 1
                 for (int j = 1; j < T; j++) {
                     u32 c[8], tmp[8];
                     ld_elem(c, v + 8 * (j - 1));
                     fp_mul<F>(tmp, s[0], c, pm);
                     fp_add<F>(s[1], s[1], tmp);
-                    // rotate lanes 1..T-1
-                    fp_copy(tmp, s[1]);
+                    fp_copy(tmp, s[1]);        // rotate lanes 1..T-1
 #pragma unroll
                     for (int q = 1; q + 1 < T; q++) fp_copy(s[q], s[q + 1]);
                     fp_copy(s[T - 1], tmp);
@@ -126,9 +132,9 @@ template <class F, int T> CPB_HD void pos_permute(u32 (&s)[T][8], const Poseidon
             if (k + 1 < P.rp) {
                 u32 c[8];
                 ld_elem(c, cs + 8 * (P.off_pc + k + 1));
-                fp_add<F>(s[0], n[T - 1], c);
+                fp_add<F>(s[0], d, c);
             } else {
-                fp_copy(s[0], n[T - 1]);
+                fp_copy(s[0], d);
             }
         }
     }

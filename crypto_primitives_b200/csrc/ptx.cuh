@@ -44,14 +44,22 @@ CPB_D void madc_wide_cc(u32& lo, u32& hi, u32 a, u32 b) {
 // (lo,hi) = a*b + (c_lo,c_hi) + CF, continuing a chain (used for the 2-limb right shift).
 CPB_D void madc_wide_cc_from(u32& lo, u32& hi, u32 a, u32 b, u32 c_lo, u32 c_hi) {
     asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;"
-                 : "=r"(lo), "=r"(hi) : "r"(a), "r"(b), "r"(c_lo), "r"(c_hi));
+                 : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b), "r"(c_lo), "r"(c_hi));
 }
 // (lo,hi) = a*b + CF; ends a chain (cannot overflow: a*b + 1 < 2^64).
 CPB_D void madc_wide_end(u32& lo, u32& hi, u32 a, u32 b) {
-    asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+// (lo,hi) = a*b + c_lo + CF; ends a chain (a*b + 2 < 2^64 when c_lo <= 1: callers pass a carry word).
+CPB_D void madc_wide_end_from(u32& lo, u32& hi, u32 a, u32 b, u32 c_lo) {
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.u32 %1, %2, %3, 0;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b), "r"(c_lo));
+}
+// (lo,hi) = a*b + c_lo; no carry in or out.
+CPB_D void mad_wide_end_from(u32& lo, u32& hi, u32 a, u32 b, u32 c_lo) {
+    asm volatile("mad.lo.cc.u32 %0, %2, %3, %4; madc.hi.u32 %1, %2, %3, 0;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b), "r"(c_lo));
 }
 CPB_D void mul_wide(u32& lo, u32& hi, u32 a, u32 b) {
-    asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+    asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b));
 }
 
 #else  // ---- host emulation (bit-exact model of the PTX carry flag) ----
@@ -81,6 +89,14 @@ inline void madc_wide_cc_from(u32& lo, u32& hi, u32 a, u32 b, u32 c_lo, u32 c_hi
 }
 inline void madc_wide_end(u32& lo, u32& hi, u32 a, u32 b) {
     u64 s = (u64)a * b + detail::cf();
+    lo = (u32)s; hi = (u32)(s >> 32);
+}
+inline void madc_wide_end_from(u32& lo, u32& hi, u32 a, u32 b, u32 c_lo) {
+    u64 s = (u64)a * b + c_lo + detail::cf();
+    lo = (u32)s; hi = (u32)(s >> 32);
+}
+inline void mad_wide_end_from(u32& lo, u32& hi, u32 a, u32 b, u32 c_lo) {
+    u64 s = (u64)a * b + c_lo;
     lo = (u32)s; hi = (u32)(s >> 32);
 }
 inline void mul_wide(u32& lo, u32& hi, u32 a, u32 b) { u64 s = (u64)a * b; lo = (u32)s; hi = (u32)(s >> 32); }

@@ -31,7 +31,9 @@ def _log2(n: int) -> int:
 
 
 class CudaPoseidonBackend:
-    """Field-leaf tree: poseidon::CRH leaves + poseidon::TwoToOneCRH nodes on the current CUDA device."""
+    """Field-leaf tree: poseidon::CRH leaves + poseidon::TwoToOneCRH nodes on the current CUDA device.
+    The returned tensors are workspaces owned by the backend: a later build with the same shape
+    overwrites them (clone what must outlive the next call)."""
 
     digest_words = 4
 
@@ -41,6 +43,14 @@ class CudaPoseidonBackend:
         self.dev = device_index
         self.leaf_ctx = leaf_params.context(device_index)
         self.node_ctx = node_params.context(device_index)
+        self._ws = {}                      # output workspaces reused across builds (no allocator traffic per step)
+
+    def _buf(self, key, shape, device):
+        t = self._ws.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.device != device:
+            t = torch.empty(shape, dtype=torch.int64, device=device)
+            self._ws[key] = t
+        return t
 
     def _stream(self):
         return torch.cuda.current_stream().cuda_stream
@@ -48,22 +58,22 @@ class CudaPoseidonBackend:
     def build_local(self, leaves: torch.Tensor):
         """leaves (n, L, 4) int64 on the GPU -> (leaf_nodes (n,4), nodes (n-1,4)) heap order."""
         n, L = leaves.shape[0], leaves.shape[1]
-        leaf_nodes = torch.empty((n, 4), dtype=torch.int64, device=leaves.device)
-        nodes = torch.empty((n - 1, 4), dtype=torch.int64, device=leaves.device)
+        leaf_nodes = self._buf("leaf", (n, 4), leaves.device)
+        nodes = self._buf("nodes", (n - 1, 4), leaves.device)
         self.N.check(self.N.lib.cpb_merkle_poseidon_build_dev(self.leaf_ctx, self.node_ctx, leaves.data_ptr(), L, n,
                                                               leaf_nodes.data_ptr(), nodes.data_ptr(), self._stream()))
         return leaf_nodes, nodes
 
     def hash_leaves(self, leaves: torch.Tensor):
         n, L = leaves.shape[0], leaves.shape[1]
-        out = torch.empty((n, 4), dtype=torch.int64, device=leaves.device)
+        out = self._buf("leaf", (n, 4), leaves.device)
         self.N.check(self.N.lib.cpb_poseidon_crh_batch_dev(self.leaf_ctx, leaves.data_ptr(), L, out.data_ptr(), n, self._stream()))
         return out
 
     def from_digests(self, digests: torch.Tensor):
         """digests (m, 4), m a power of two >= 2 -> (m-1, 4) heap-ordered inner nodes."""
         m = digests.shape[0]
-        nodes = torch.empty((m - 1, 4), dtype=torch.int64, device=digests.device)
+        nodes = self._buf("top", (m - 1, 4), digests.device)
         self.N.check(self.N.lib.cpb_merkle_poseidon_from_digests_dev(self.node_ctx, digests.data_ptr(), m, nodes.data_ptr(),
                                                                      self._stream()))
         return nodes

@@ -28,10 +28,11 @@ def _val(a):
 def test_field_ops(shim, fid, name):
     p = MODULI[name]
     rnd = random.Random(fid)
-    n = 600
+    n = 800
     A = [rnd.randrange(p) for _ in range(n)]
     B = [rnd.randrange(p) for _ in range(n)]
-    edge = [0, 1, 2, p - 1, p - 2, (1 << 255) % p, (1 << 256) % p, p >> 1]
+    edge = [0, 1, 2, p - 1, p - 2, (1 << 255) % p, (1 << 256) % p, p >> 1,
+            (0xDEADBEEF << 32) % p, (0x1234567 << 64) % p, (7 << 224) % p, (p - 1) & ~0xFFFFFFFF]   # zero low limbs: m == 0 rows
     for i, (x, y) in enumerate((x, y) for x in edge for y in edge):
         A[i], B[i] = x, y
     a = np.array([_limbs(x) for x in A], dtype=np.uint32)
