@@ -12,9 +12,7 @@
 // CTA; inputs are read with 128-bit loads; state lives in registers.
 #include <vector>
 
-#include "common.cuh"
-#include "poseidon.cuh"
-#include "poseidon_host.hpp"
+#include "poseidon_kernels.cuh"
 
 namespace cpb {
 
@@ -43,51 +41,6 @@ int sm_count(int device) {
         cache[device] = v;
     }
     return cache[device];
-}
-
-// ------------------------------------------------------------------------------ kernels
-constexpr int kBlock = 128;
-#ifndef CPB_POS_MINBLOCKS
-#define CPB_POS_MINBLOCKS 5
-#endif
-
-template <class F, int T>
-__global__ void __launch_bounds__(kBlock, CPB_POS_MINBLOCKS)
-k_poseidon_crh(PoseidonDev P, const u32* __restrict__ consts, const u32* __restrict__ in, u32* __restrict__ out,
-               long n, long len) {
-    extern __shared__ __align__(16) u32 cs[];
-    __shared__ __align__(8) unsigned long long mbar;
-    tma_stage_to_smem(cs, consts, (unsigned)P.n_elems * 32u, &mbar);
-    const u32* ct = cs + (int)threadIdx.x * P.zero;   // == cs, but not provably warp-uniform
-    u32 pm[8];
-    ld_elem(pm, ct + 8 * P.off_mod);
-    const long stride = (long)gridDim.x * blockDim.x;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        u32 r[8];
-        pos_crh<F, T>(r, in + 8 * len * i, len, P, ct, pm);
-        st_elem(out + 8 * i, r);
-    }
-}
-
-template <class F, int T>
-__global__ void __launch_bounds__(kBlock, CPB_POS_MINBLOCKS)
-k_poseidon_permute(PoseidonDev P, const u32* __restrict__ consts, const u32* __restrict__ in, u32* __restrict__ out,
-                   long n) {
-    extern __shared__ __align__(16) u32 cs[];
-    __shared__ __align__(8) unsigned long long mbar;
-    tma_stage_to_smem(cs, consts, (unsigned)P.n_elems * 32u, &mbar);
-    const u32* ct = cs + (int)threadIdx.x * P.zero;
-    u32 pm[8];
-    ld_elem(pm, ct + 8 * P.off_mod);
-    const long stride = (long)gridDim.x * blockDim.x;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        u32 s[T][8];
-#pragma unroll
-        for (int j = 0; j < T; j++) ld_elem(s[j], in + 8 * (T * i + j));
-        pos_permute<F, T>(s, P, ct, pm);
-#pragma unroll
-        for (int j = 0; j < T; j++) st_elem(out + 8 * (T * i + j), s[j]);
-    }
 }
 
 template <class F>
@@ -123,16 +76,14 @@ __global__ void k_field_convert(const u32* __restrict__ in, u32* __restrict__ ou
 
 using namespace cpb;
 
-// ------------------------------------------------------------------------------ context
-struct cpb_poseidon_ctx {
-    int field_id = 0, device = 0, sms = 148;
-    host::PoseidonSchedule sched;
-    PoseidonDev dev{};
-    u32* d_consts = nullptr;
-    cudaStream_t stream = nullptr;
-    std::mutex mu;
-    Scratch s_in, s_out, s_aux;
-};
+using namespace cpb;
+
+namespace cpb {
+CPB_POS_WIDTHS(CPB_POS_EXTERN, Bls12_381_Fr)
+CPB_POS_WIDTHS(CPB_POS_EXTERN, Bn254_Fr)
+CPB_POS_WIDTHS(CPB_POS_EXTERN, Jubjub_Fr)
+CPB_POS_WIDTHS(CPB_POS_EXTERN, Bls12_377_Fr)
+}  // namespace cpb
 
 namespace {
 
@@ -144,60 +95,32 @@ PoseidonDev to_dev(const host::PoseidonSchedule& S) {
     return D;
 }
 
-template <class K> cpb_status grid_for(K kernel, size_t smem, int sms, long n, int& grid) {
-    static thread_local const void* last = nullptr;
-    static thread_local int last_occ = 0;
-    static thread_local size_t last_smem = 0;
-    if (last != (const void*)kernel || last_smem != smem) {
-        if (smem > 48 * 1024) CPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 0;
-        CPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, smem));
-        if (occ < 1) return fail(CPB_CUDA_ERROR, "kernel does not fit on an SM (smem=%zu)", smem);
-        last = (const void*)kernel; last_occ = occ; last_smem = smem;
-    }
-    long need = (n + kBlock - 1) / kBlock;
-    long cap = (long)sms * last_occ;     // persistent: one wave, grid-stride inside
-    grid = (int)(need < cap ? need : cap);
-    if (grid < 1) grid = 1;
-    return CPB_OK;
-}
 
-template <class F, int T>
-cpb_status launch_crh_ft(cpb_poseidon_ctx* c, const u32* in, size_t len, u32* out, size_t n, cudaStream_t st) {
-    size_t smem = (size_t)c->dev.n_elems * 32;
-    int grid = 1;
-    CPB_TRY(grid_for(k_poseidon_crh<F, T>, smem, c->sms, (long)n, grid));
-    k_poseidon_crh<F, T><<<grid, kBlock, smem, st>>>(c->dev, c->d_consts, in, out, (long)n, (long)len);
-    CPB_CUDA(cudaGetLastError());
-    return CPB_OK;
-}
-template <class F, int T>
-cpb_status launch_permute_ft(cpb_poseidon_ctx* c, const u32* in, u32* out, size_t n, cudaStream_t st) {
-    size_t smem = (size_t)c->dev.n_elems * 32;
-    int grid = 1;
-    CPB_TRY(grid_for(k_poseidon_permute<F, T>, smem, c->sms, (long)n, grid));
-    k_poseidon_permute<F, T><<<grid, kBlock, smem, st>>>(c->dev, c->d_consts, in, out, (long)n);
-    CPB_CUDA(cudaGetLastError());
-    return CPB_OK;
-}
-
-#define CPB_FOR_FIELD(fid, M, ...)                                                      \
-    switch (fid) {                                                                      \
-        case CPB_BLS12_381_FR: return M<Bls12_381_Fr, 3>(__VA_ARGS__);                  \
-        case CPB_BN254_FR: return M<Bn254_Fr, 3>(__VA_ARGS__);                          \
-        case CPB_JUBJUB_FR: return M<Jubjub_Fr, 3>(__VA_ARGS__);                        \
-        case CPB_BLS12_377_FR: return M<Bls12_377_Fr, 3>(__VA_ARGS__);                  \
+#define CPB_CASE_T(F, T, M, ...) case T: return M<F, T>(__VA_ARGS__);
+#define CPB_FOR_T(F, M, ...)                                                                                   \
+    switch (c->dev.t) {                                                                                        \
+        CPB_CASE_T(F, 2, M, __VA_ARGS__) CPB_CASE_T(F, 3, M, __VA_ARGS__) CPB_CASE_T(F, 4, M, __VA_ARGS__)     \
+        CPB_CASE_T(F, 5, M, __VA_ARGS__) CPB_CASE_T(F, 6, M, __VA_ARGS__) CPB_CASE_T(F, 7, M, __VA_ARGS__)     \
+        CPB_CASE_T(F, 8, M, __VA_ARGS__) CPB_CASE_T(F, 9, M, __VA_ARGS__)                                      \
+    }                                                                                                          \
+    break;
+#define CPB_FOR_FIELD(M, ...)                                                        \
+    switch (c->field_id) {                                                           \
+        case CPB_BLS12_381_FR: CPB_FOR_T(Bls12_381_Fr, M, __VA_ARGS__)               \
+        case CPB_BN254_FR: CPB_FOR_T(Bn254_Fr, M, __VA_ARGS__)                       \
+        case CPB_JUBJUB_FR: CPB_FOR_T(Jubjub_Fr, M, __VA_ARGS__)                     \
+        case CPB_BLS12_377_FR: CPB_FOR_T(Bls12_377_Fr, M, __VA_ARGS__)               \
     }
 
 cpb_status launch_crh(cpb_poseidon_ctx* c, const u32* in, size_t len, u32* out, size_t n, cudaStream_t st) {
     if (n == 0) return CPB_OK;
-    if (c->dev.t == 3) { CPB_FOR_FIELD(c->field_id, launch_crh_ft, c, in, len, out, n, st) }
-    return fail(CPB_UNSUPPORTED, "state width t=%d not built (this build: t=3)", c->dev.t);
+    CPB_FOR_FIELD(launch_crh_ft, c, in, len, out, n, st)
+    return fail(CPB_UNSUPPORTED, "state width t=%d is not built (this library: t = 2..9)", c->dev.t);
 }
 cpb_status launch_permute(cpb_poseidon_ctx* c, const u32* in, u32* out, size_t n, cudaStream_t st) {
     if (n == 0) return CPB_OK;
-    if (c->dev.t == 3) { CPB_FOR_FIELD(c->field_id, launch_permute_ft, c, in, out, n, st) }
-    return fail(CPB_UNSUPPORTED, "state width t=%d not built (this build: t=3)", c->dev.t);
+    CPB_FOR_FIELD(launch_permute_ft, c, in, out, n, st)
+    return fail(CPB_UNSUPPORTED, "state width t=%d is not built (this library: t = 2..9)", c->dev.t);
 }
 
 cpb_status check_ctx(const cpb_poseidon_ctx* c) {

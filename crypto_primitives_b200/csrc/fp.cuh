@@ -189,7 +189,7 @@ template <class F, bool WITH_X> CPB_HD void redc_row_impl(u32* E, u32* O, u32* X
     } else if (F::P0_POW > 0) {
         // p[0] = 2^32 - 2^k + 1 (BN254 Fr, k = 28): -p^-1 = -(1 + 2^k) mod 2^32 and m*p[0] are shifts and
         // adds on the idle ALU pipe instead of an IMAD and an IMAD.HI on the saturated multiply pipe.
-        constexpr int K = F::P0_POW;
+        constexpr int K = F::P0_POW > 0 ? F::P0_POW : 1;   // (branch is dead when P0_POW == 0)
         const u32 e0 = E[0];
         const u32 m = 0u - (e0 + (e0 << K));
         // B = m * (2^k - 1);  m*p[0] = m*2^32 - B;  hi(m*p[0] + e0) = m - B_hi - [B_lo != 0] + [e0 != 0]

@@ -1,0 +1,119 @@
+// poseidon_kernels.cuh -- Poseidon kernel templates, the context struct and the launch wrappers.
+// Included by cpb_poseidon.cu (C-ABI, dispatch) and by the per-field instantiation units
+// poseidon_inst_*.cu, which exist only so that nvcc can compile the (field, width) grid in parallel.
+#pragma once
+#include <mutex>
+
+#include "common.cuh"
+#include "poseidon.cuh"
+#include "poseidon_host.hpp"
+
+namespace cpb {
+
+constexpr int kBlock = 128;
+// resident CTAs per SM the register allocator must allow: 5 for the narrow states (96 registers), 1 for wide ones
+constexpr int pos_min_blocks(int t) { return t <= 3 ? 5 : t <= 5 ? 3 : 1; }
+
+template <class F, int T>
+__global__ void __launch_bounds__(kBlock, pos_min_blocks(T))
+k_poseidon_crh(PoseidonDev P, const u32* __restrict__ consts, const u32* __restrict__ in, u32* __restrict__ out,
+               long n, long len) {
+    extern __shared__ __align__(16) u32 cs[];
+    __shared__ __align__(8) unsigned long long mbar;
+    tma_stage_to_smem(cs, consts, (unsigned)P.n_elems * 32u, &mbar);
+    const u32* ct = cs + (int)threadIdx.x * P.zero;   // == cs, but not provably warp-uniform
+    u32 pm[8];
+    ld_elem(pm, ct + 8 * P.off_mod);
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        u32 r[8];
+        pos_crh<F, T>(r, in + 8 * len * i, len, P, ct, pm);
+        st_elem(out + 8 * i, r);
+    }
+}
+
+template <class F, int T>
+__global__ void __launch_bounds__(kBlock, pos_min_blocks(T))
+k_poseidon_permute(PoseidonDev P, const u32* __restrict__ consts, const u32* __restrict__ in, u32* __restrict__ out,
+                   long n) {
+    extern __shared__ __align__(16) u32 cs[];
+    __shared__ __align__(8) unsigned long long mbar;
+    tma_stage_to_smem(cs, consts, (unsigned)P.n_elems * 32u, &mbar);
+    const u32* ct = cs + (int)threadIdx.x * P.zero;
+    u32 pm[8];
+    ld_elem(pm, ct + 8 * P.off_mod);
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        u32 s[T][8];
+#pragma unroll
+        for (int j = 0; j < T; j++) ld_elem(s[j], in + 8 * (T * i + j));
+        pos_permute<F, T>(s, P, ct, pm);
+#pragma unroll
+        for (int j = 0; j < T; j++) st_elem(out + 8 * (T * i + j), s[j]);
+    }
+}
+
+}  // namespace cpb
+
+struct cpb_poseidon_ctx {
+    typedef cpb::u32 u32;
+    int field_id = 0, device = 0, sms = 148;
+    cpb::host::PoseidonSchedule sched;
+    cpb::PoseidonDev dev{};
+    u32* d_consts = nullptr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    cpb::Scratch s_in, s_out, s_aux;
+};
+
+
+namespace cpb {
+
+template <class K> cpb_status grid_for(K kernel, size_t smem, int sms, long n, int& grid) {
+    static thread_local const void* last = nullptr;
+    static thread_local int last_occ = 0;
+    static thread_local size_t last_smem = 0;
+    if (last != (const void*)kernel || last_smem != smem) {
+        if (smem > 48 * 1024) CPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, smem));
+        if (occ < 1) return fail(CPB_CUDA_ERROR, "kernel does not fit on an SM (smem=%zu)", smem);
+        last = (const void*)kernel; last_occ = occ; last_smem = smem;
+    }
+    long need = (n + kBlock - 1) / kBlock;
+    long cap = (long)sms * last_occ;     // persistent: one wave, grid-stride inside
+    grid = (int)(need < cap ? need : cap);
+    if (grid < 1) grid = 1;
+    return CPB_OK;
+}
+
+template <class F, int T>
+cpb_status launch_crh_ft(cpb_poseidon_ctx* c, const u32* in, size_t len, u32* out, size_t n, cudaStream_t st) {
+    size_t smem = (size_t)c->dev.n_elems * 32;
+    int grid = 1;
+    CPB_TRY(grid_for(k_poseidon_crh<F, T>, smem, c->sms, (long)n, grid));
+    k_poseidon_crh<F, T><<<grid, kBlock, smem, st>>>(c->dev, c->d_consts, in, out, (long)n, (long)len);
+    CPB_CUDA(cudaGetLastError());
+    return CPB_OK;
+}
+template <class F, int T>
+cpb_status launch_permute_ft(cpb_poseidon_ctx* c, const u32* in, u32* out, size_t n, cudaStream_t st) {
+    size_t smem = (size_t)c->dev.n_elems * 32;
+    int grid = 1;
+    CPB_TRY(grid_for(k_poseidon_permute<F, T>, smem, c->sms, (long)n, grid));
+    k_poseidon_permute<F, T><<<grid, kBlock, smem, st>>>(c->dev, c->d_consts, in, out, (long)n);
+    CPB_CUDA(cudaGetLastError());
+    return CPB_OK;
+}
+
+
+// explicit instantiations live in poseidon_inst_<field>.cu
+#define CPB_POS_WIDTHS(M, F) M(F, 2) M(F, 3) M(F, 4) M(F, 5) M(F, 6) M(F, 7) M(F, 8) M(F, 9)
+#define CPB_POS_INSTANTIATE(F, T)                                                                                        \
+    template cpb_status launch_crh_ft<F, T>(cpb_poseidon_ctx*, const u32*, size_t, u32*, size_t, cudaStream_t);            \
+    template cpb_status launch_permute_ft<F, T>(cpb_poseidon_ctx*, const u32*, u32*, size_t, cudaStream_t);
+#define CPB_POS_EXTERN(F, T)                                                                                             \
+    extern template cpb_status launch_crh_ft<F, T>(cpb_poseidon_ctx*, const u32*, size_t, u32*, size_t, cudaStream_t);     \
+    extern template cpb_status launch_permute_ft<F, T>(cpb_poseidon_ctx*, const u32*, u32*, size_t, cudaStream_t);
+
+}  // namespace cpb

@@ -61,6 +61,35 @@ def test_two_to_one_and_permute_match_oracle(which):
     assert np.array_equal(permute_batch(cfg, st), exp)
 
 
+@pytest.mark.parametrize("rate,weights", [(1, None), (3, False), (4, False), (5, False), (6, True), (7, False), (8, False), (8, True)])
+def test_other_state_widths(rate, weights):
+    """t = 2..9: the reference's default-parameter table covers rates 2..8 (R/sponge/test.rs:13-32);
+    rate 1 uses a random parameter set.  CRH over ragged lengths, two-to-one, bare permutation."""
+    from oracle import fields as OF
+    p = OF.BLS12_381_FR
+    if weights is None:
+        rng = OF.SplitMix64(1)
+        ocfg = OP.PoseidonConfig(p, 4, 3, 17, [[rng.field(p) for _ in range(2)] for _ in range(7)],
+                                 [[rng.field(p) for _ in range(2)] for _ in range(2)], 1, 1)
+    else:
+        ocfg = OP.get_default_poseidon_parameters(p, rate, weights)
+    cfg = cp.PoseidonConfig.from_ints(cp.BLS12_381_FR, ocfg.full_rounds, ocfg.partial_rounds, ocfg.alpha, ocfg.mds, ocfg.ark,
+                                      ocfg.rate, ocfg.capacity)
+    O = cref.Poseidon(ocfg)
+    t = rate + 1
+    for L in (0, 1, rate, rate + 1, 3 * rate + 2):
+        x = np.ascontiguousarray(synth_elems(2000 + L, (129, max(L, 1)), p)[:, :L])
+        assert np.array_equal(CRH.evaluate_batch(cfg, x), O.crh_batch(x, threads=8)), (rate, L)
+    st = synth_elems(2100, (65, t), p)
+    assert np.array_equal(permute_batch(cfg, st), np.stack([O.permute(s) for s in st]))
+    if rate >= 2:
+        pairs = synth_elems(2200, (200, 2), p)
+        assert np.array_equal(TwoToOneCRH.compress_batch(cfg, pairs), O.compress_batch(pairs, threads=8))
+    else:
+        with pytest.raises(N.CpbError):
+            TwoToOneCRH.compress_batch(cfg, synth_elems(1, (2, 2), p))     # rate 1: two absorbs are not one permutation
+
+
 def test_empty_batch_and_bad_args():
     cfg = product_config("bls_default_r2")
     assert CRH.evaluate_batch(cfg, np.zeros((0, 2, 4), dtype=np.uint64)).shape == (0, 4)
