@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_obj")
+OBJ = os.environ.get("CPB_OBJ_DIR", os.path.join("/tmp", "cpb200_obj"))     # objects stay out of the tree (the .so is the artefact)
 LIB = os.path.join(HERE, os.environ.get("CPB_LIB_NAME", "libcpb200.so"))
 EXTRA = os.environ.get("CPB_NVCC_EXTRA", "").split()
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -10,6 +10,7 @@
 //   k_field_convert     canonical <-> Montgomery.
 // Round constants / MDS / sparse rows are staged into shared memory with one TMA bulk copy per
 // CTA; inputs are read with 128-bit loads; state lives in registers.
+#include <cstdlib>
 #include <vector>
 
 #include "poseidon_kernels.cuh"
@@ -128,14 +129,86 @@ cpb_status check_ctx(const cpb_poseidon_ctx* c) {
     return CPB_OK;
 }
 
-// heap-ordered inner levels from n leaf digests (new_with_leaf_digest, R/merkle_tree/mod.rs:424-523)
+// Inner levels of subtree k of S (S a power of two) from the leaf digests, heap order: global level l has
+// 2^l nodes at [2^l - 1, 2^(l+1) - 1); subtree k owns the k-th 1/S of every level l >= log2 S
+// (new_with_leaf_digest, R/merkle_tree/mod.rs:424-523).  S = 1, k = 0 is the whole tree.
+cpb_status merkle_subtree_levels(cpb_poseidon_ctx* node, const u32* leaf_digests, size_t n, u32* nodes, size_t S, size_t k,
+                                 cudaStream_t st) {
+    int h = 0;
+    while (((size_t)1 << h) < n) h++;
+    int lg = 0;
+    while (((size_t)1 << lg) < S) lg++;
+    for (int l = h - 1; l >= lg; l--) {
+        size_t cnt = ((size_t)1 << l) / S;
+        const u32* in = (l == h - 1) ? leaf_digests + 8 * (2 * k * cnt) : nodes + 8 * ((((size_t)1 << (l + 1)) - 1) + 2 * k * cnt);
+        u32* out = nodes + 8 * ((((size_t)1 << l) - 1) + k * cnt);
+        CPB_TRY(launch_crh(node, in, 2, out, cnt, st));
+    }
+    return CPB_OK;
+}
 cpb_status merkle_levels(cpb_poseidon_ctx* node, const u32* leaf_digests, size_t n, u32* nodes, cudaStream_t st) {
-    size_t start = n / 2 - 1;
-    CPB_TRY(launch_crh(node, leaf_digests, 2, nodes + 8 * start, n / 2, st));
-    while (start > 0) {
-        size_t upper = start;
-        start = (start - 1) / 2;
-        CPB_TRY(launch_crh(node, nodes + 8 * upper, 2, nodes + 8 * start, upper - start, st));
+    return merkle_subtree_levels(node, leaf_digests, n, nodes, 1, 0, st);
+}
+
+// Number of concurrently built subtrees: the top ~16 levels of a tree are latency-bound (fewer nodes than
+// thread slots, one single-warp permutation latency each); building S subtrees on S streams hides the
+// tails of all but the last behind bulk work.  CPB_MERKLE_STREAMS overrides (1 disables).
+size_t merkle_streams(size_t n) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("CPB_MERKLE_STREAMS");
+        forced = e ? atoi(e) : 0;
+    }
+    size_t S = forced > 0 ? (size_t)forced : 8;
+    if (S > 8) S = 8;
+    while (S & (S - 1)) S &= S - 1;
+    while (S > 1 && n / S < ((size_t)1 << 14)) S >>= 1;
+    return S;
+}
+
+cpb_status ensure_side_streams(cpb_poseidon_ctx* c, size_t S) {
+    std::lock_guard<std::mutex> lk(c->side_mu);
+    for (size_t i = 0; i < S; i++)
+        if (!c->side[i]) CPB_CUDA(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+    return CPB_OK;
+}
+
+// leaf hashing (when leaves != nullptr) + all inner levels, S subtrees on S side streams joined on `st`
+cpb_status merkle_build_streams(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, const u32* leaves, size_t leaf_len, size_t n,
+                                u32* leaf_nodes, u32* nodes, cudaStream_t st) {
+    size_t S = merkle_streams(n);
+    if (S <= 1) {
+        if (leaves) CPB_TRY(launch_crh(leaf, leaves, leaf_len, leaf_nodes, n, st));
+        return merkle_levels(node, leaf_nodes, n, nodes, st);
+    }
+    CPB_TRY(ensure_side_streams(node, S));
+    cudaEvent_t start = nullptr, done[8] = {};
+    CPB_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(start, st);
+    cpb_status rc = CPB_OK;
+    size_t per = n / S;
+    for (size_t k = 0; k < S && e == cudaSuccess && rc == CPB_OK; k++) {
+        cudaStream_t sk = node->side[k];
+        e = cudaStreamWaitEvent(sk, start, 0);
+        if (e != cudaSuccess) break;
+        if (leaves) rc = launch_crh(leaf, leaves + 8 * leaf_len * (k * per), leaf_len, leaf_nodes + 8 * (k * per), per, sk);
+        if (rc == CPB_OK) rc = merkle_subtree_levels(node, leaf_nodes, n, nodes, S, k, sk);
+        if (rc != CPB_OK) break;
+        e = cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(done[k], sk);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, done[k], 0);
+    }
+    cudaEventDestroy(start);
+    for (size_t k = 0; k < S; k++)
+        if (done[k]) cudaEventDestroy(done[k]);
+    if (rc != CPB_OK) return rc;
+    if (e != cudaSuccess) return fail(CPB_CUDA_ERROR, "merkle stream fork/join failed: %s", cudaGetErrorString(e));
+    // top log2(S) levels on the caller's stream
+    int lg = 0;
+    while (((size_t)1 << lg) < S) lg++;
+    for (int l = lg - 1; l >= 0; l--) {
+        size_t cnt = (size_t)1 << l;
+        CPB_TRY(launch_crh(node, nodes + 8 * ((((size_t)1 << (l + 1)) - 1)), 2, nodes + 8 * (cnt - 1), cnt, st));
     }
     return CPB_OK;
 }
@@ -286,6 +359,8 @@ void cpb_poseidon_ctx_destroy(cpb_poseidon_ctx* c) {
     DeviceGuard g(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     if (c->d_consts) cudaFree(c->d_consts);
+    for (auto& s : c->side)
+        if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     c->s_in.release(); c->s_out.release(); c->s_aux.release();
     delete c;
 }
@@ -318,7 +393,7 @@ cpb_status cpb_merkle_poseidon_from_digests_dev(cpb_poseidon_ctx* node, const ui
     if (!pow2_gt1(n)) return fail(CPB_NOT_POW2, "leaves.len() should be power of two and greater than one (got %zu)", n);
     if (node->dev.rate < 2) return fail(CPB_UNSUPPORTED, "two-to-one with rate < 2 not supported");
     DeviceGuard g(node->device);
-    return merkle_levels(node, (const u32*)leaf_digests, n, (u32*)non_leaf_nodes, (cudaStream_t)stream);
+    return merkle_build_streams(node, node, nullptr, 0, n, (u32*)leaf_digests, (u32*)non_leaf_nodes, (cudaStream_t)stream);
 }
 cpb_status cpb_merkle_poseidon_build_dev(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, const uint64_t* leaves,
                                          size_t leaf_len, size_t n, uint64_t* leaf_nodes, uint64_t* non_leaf_nodes,
@@ -330,8 +405,8 @@ cpb_status cpb_merkle_poseidon_build_dev(cpb_poseidon_ctx* leaf, cpb_poseidon_ct
     if (!pow2_gt1(n)) return fail(CPB_NOT_POW2, "leaves.len() should be power of two and greater than one (got %zu)", n);
     if (node->dev.rate < 2) return fail(CPB_UNSUPPORTED, "two-to-one with rate < 2 not supported");
     DeviceGuard g(leaf->device);
-    CPB_TRY(launch_crh(leaf, (const u32*)leaves, leaf_len, (u32*)leaf_nodes, n, (cudaStream_t)stream));
-    return merkle_levels(node, (const u32*)leaf_nodes, n, (u32*)non_leaf_nodes, (cudaStream_t)stream);
+    return merkle_build_streams(leaf, node, (const u32*)leaves, leaf_len, n, (u32*)leaf_nodes, (u32*)non_leaf_nodes,
+                                (cudaStream_t)stream);
 }
 
 // ---- host-pointer entry points: H2D, launch, D2H on the context stream

@@ -66,6 +66,11 @@ template <class F, int T> CPB_HD void pos_permute(u32 (&s)[T][8], const Poseidon
     for (int i = 63; i > 0; i--)
         if ((P.alpha >> i) & 1) { top_bit = i; break; }
     const bool alpha_zero = P.alpha == 0;
+    // row collector of the dense layers; defined once so that the shift below never reads an
+    // indeterminate value (with the array declared inside the loop nvcc miscompiled t >= 5)
+    u32 n[T][8];
+#pragma unroll
+    for (int i = 0; i < T; i++) fp_zero(n[i]);
 #pragma unroll 1
     for (int r = 0; r < total; r++) {
         const bool full = r < half || r >= half + P.rp;
@@ -92,7 +97,7 @@ template <class F, int T> CPB_HD void pos_permute(u32 (&s)[T][8], const Poseidon
         const u32* rows = dense ? cs + 8 * ((full && r == half - 1) ? P.off_mpre : P.off_m)
                                 : cs + 8 * (P.off_sp + k * (2 * T - 1));
         const int nrows = dense ? T : 1;
-        u32 n[T][8], d[8];
+        u32 d[8];
 #pragma unroll 1
         for (int i = 0; i < nrows; i++) {
             fp_dot<F, T>(d, s, rows + 8 * T * i, pm);
@@ -108,7 +113,10 @@ template <class F, int T> CPB_HD void pos_permute(u32 (&s)[T][8], const Poseidon
         } else {
             // s_j += v_j * s_0 for j >= 1 (old s_0), then s_0 <- row product d (+ next lane-0 constant)
             const u32* v = rows + 8 * T;
-            if (T <= 4) {
+#ifndef CPB_COL_UNROLL_MAX
+#define CPB_COL_UNROLL_MAX 4
+#endif
+            if (T <= CPB_COL_UNROLL_MAX) {
 #pragma unroll
                 for (int j = 1; j < T; j++) {
                     u32 c[8], tmp[8];

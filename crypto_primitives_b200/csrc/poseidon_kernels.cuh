@@ -64,6 +64,8 @@ struct cpb_poseidon_ctx {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     cpb::Scratch s_in, s_out, s_aux;
+    std::mutex side_mu;                 // guards creation of side[] only (mu may already be held by a host-pointer call)
+    cudaStream_t side[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // subtree streams of the Merkle build
 };
 
 
@@ -80,8 +82,11 @@ template <class K> cpb_status grid_for(K kernel, size_t smem, int sms, long n, i
         if (occ < 1) return fail(CPB_CUDA_ERROR, "kernel does not fit on an SM (smem=%zu)", smem);
         last = (const void*)kernel; last_occ = occ; last_smem = smem;
     }
+    // One CTA per 128 hashes (capped; the kernels grid-stride).  Short-lived CTAs instead of one persistent
+    // wave let the block scheduler interleave kernels from different streams: the latency-bound top
+    // levels of one Merkle subtree then overlap with the bulk hashing of the next (merkle build).
     long need = (n + kBlock - 1) / kBlock;
-    long cap = (long)sms * last_occ;     // persistent: one wave, grid-stride inside
+    long cap = (long)sms * last_occ * 64;
     grid = (int)(need < cap ? need : cap);
     if (grid < 1) grid = 1;
     return CPB_OK;
