@@ -82,32 +82,33 @@ static void fe_sub(const field_t *F, fe *r, const fe *a, const fe *b) {
     memcpy(r->l, t, 32);
 }
 
-/* Montgomery product a*b/R mod p (CIOS, 64-bit limbs). */
-static void fe_mul(const field_t *F, fe *r, const fe *a, const fe *b) {
-    u64 t[6] = {0, 0, 0, 0, 0, 0};
+/* Montgomery product a*b/R mod p (CIOS, 64-bit limbs), unrolled; the compiler keeps t[] in registers
+ * and emits mulx/adcx-style code with -march=x86-64-v3 (ark-ff's own mul is generated the same way). */
+#define MAC(acc, x, y, carry)                                  \
+    do {                                                       \
+        u128 s__ = (u128)(x) * (y) + (acc) + (carry);          \
+        (acc) = (u64)s__;                                      \
+        (carry) = (u64)(s__ >> 64);                            \
+    } while (0)
+static inline void fe_mul(const field_t *F, fe *r, const fe *a, const fe *b) {
+    const u64 p0 = F->p[0], p1 = F->p[1], p2 = F->p[2], p3 = F->p[3], ninv = F->ninv;
+    const u64 a0 = a->l[0], a1 = a->l[1], a2 = a->l[2], a3 = a->l[3];
+    u64 t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
     for (int i = 0; i < 4; i++) {
-        u64 c = 0;
-        for (int j = 0; j < 4; j++) {
-            u128 s = (u128)a->l[j] * b->l[i] + t[j] + c;
-            t[j] = (u64)s;
-            c = (u64)(s >> 64);
-        }
-        u128 s = (u128)t[4] + c;
-        t[4] = (u64)s;
-        t[5] = (u64)(s >> 64);
-        u64 m = t[0] * F->ninv;
-        s = (u128)m * F->p[0] + t[0];
-        c = (u64)(s >> 64);
-        for (int j = 1; j < 4; j++) {
-            s = (u128)m * F->p[j] + t[j] + c;
-            t[j - 1] = (u64)s;
-            c = (u64)(s >> 64);
-        }
-        s = (u128)t[4] + c;
-        t[3] = (u64)s;
-        t[4] = t[5] + (u64)(s >> 64);
+        const u64 bi = b->l[i];
+        u64 c = 0, t5;
+        MAC(t0, a0, bi, c); MAC(t1, a1, bi, c); MAC(t2, a2, bi, c); MAC(t3, a3, bi, c);
+        { u128 s = (u128)t4 + c; t4 = (u64)s; t5 = (u64)(s >> 64); }
+        const u64 m = t0 * ninv;
+        c = 0;
+        { u64 lo = t0; MAC(lo, m, p0, c); }
+        { u64 v = t1; MAC(v, m, p1, c); t0 = v; }
+        { u64 v = t2; MAC(v, m, p2, c); t1 = v; }
+        { u64 v = t3; MAC(v, m, p3, c); t2 = v; }
+        { u128 s = (u128)t4 + c; t3 = (u64)s; t4 = t5 + (u64)(s >> 64); }
     }
-    if (t[4] || ge4(t, F->p)) sub4(t, t, F->p);
+    u64 t[4] = {t0, t1, t2, t3};
+    if (t4 || ge4(t, F->p)) sub4(t, t, F->p);
     memcpy(r->l, t, 32);
 }
 
