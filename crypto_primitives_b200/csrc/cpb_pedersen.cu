@@ -6,8 +6,9 @@
 //                      list, normalised to affine-Niels entries (96 B each).
 //   k_pedersen_hash    one hash per thread: for every input byte, one table lookup + one 7M mixed
 //                      addition; the chunk's 24 KB table slice is staged in shared memory by TMA
-//                      bulk copies, double-buffered against the additions; the final projective ->
-//                      affine conversion shares one field inversion per warp (shuffle product tree).
+//                      bulk copies, double-buffered against the additions; output projective.
+//   k_pedersen_normalise projective -> affine with one field inversion per 32 points (Montgomery's trick along
+//                      each thread's own sequence of points).
 //   k_points_to_bytes  serialize_uncompressed of child digests for TwoToOneCRH::compress
 //                      (R/crh/pedersen/mod.rs:187-197, R/macros.rs:3-13): canonical x || y.
 #include <vector>
@@ -64,47 +65,6 @@ k_pedersen_table(const u32* __restrict__ consts, const u32* __restrict__ gens_xy
     st_elem(o + 16, t2d);
 }
 
-__device__ __forceinline__ void shfl_elem(u32* r, const u32* a, int src_lane) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) r[i] = __shfl_sync(0xffffffffu, a[i], src_lane);
-}
-
-// 1/z for the 32 lanes of a warp with a single inversion: prefix and suffix product scans over the
-// warp, invert the total (every lane computes the same value -- free in SIMT), recombine.
-// All 32 lanes must call this; z must be non-zero (pass one for idle lanes).
-template <class F> __device__ __forceinline__ void warp_batch_inverse(u32* zinv, const u32* z, const u32* pm) {
-    const int lane = threadIdx.x & 31;
-    u32 pre[8], suf[8], t[8], m[8];
-    fp_copy(pre, z);
-    fp_copy(suf, z);
-#pragma unroll 1
-    for (int off = 1; off < 32; off <<= 1) {
-        int src = lane - off;
-        shfl_elem(t, pre, src < 0 ? lane : src);
-        fp_mul<F>(m, pre, t, pm);
-#pragma unroll
-        for (int i = 0; i < 8; i++) pre[i] = src >= 0 ? m[i] : pre[i];
-        src = lane + off;
-        shfl_elem(t, suf, src > 31 ? lane : src);
-        fp_mul<F>(m, suf, t, pm);
-#pragma unroll
-        for (int i = 0; i < 8; i++) suf[i] = src <= 31 ? m[i] : suf[i];
-    }
-    u32 total[8], inv[8], left[8], right[8], one[8];
-    shfl_elem(total, pre, 31);
-    fp_inv<F>(inv, total, pm);
-    fp_one<F>(one);
-    shfl_elem(left, pre, lane > 0 ? lane - 1 : lane);
-    shfl_elem(right, suf, lane < 31 ? lane + 1 : lane);
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        left[i] = lane > 0 ? left[i] : one[i];
-        right[i] = lane < 31 ? right[i] : one[i];
-    }
-    fp_mul<F>(t, left, right, pm);
-    fp_mul<F>(zinv, t, inv, pm);
-}
-
 // 16 input bytes starting at `off` of a `len`-byte message (zero beyond len), as 4 LE words.
 __device__ __forceinline__ void load16(u32* w, const uint8_t* base, long off, long len) {
     const uint8_t* p = base + off;
@@ -125,12 +85,12 @@ __device__ __forceinline__ void load16(u32* w, const uint8_t* base, long off, lo
     }
 }
 
-// mode 0: out = n x (x, y); mode 1: out = n x x (TECompressor, R/crh/injective_map/mod.rs:24-31)
+// out = n x (X, Y, Z, -) projective, 32 words per hash (normalised by k_pedersen_normalise)
 template <class F>
 __global__ void __launch_bounds__(kPedBlock)
 k_pedersen_hash(PedersenDev P, const u32* __restrict__ consts, const u32* __restrict__ table,
                 const uint8_t* __restrict__ in, long len, long stride, const uint8_t* __restrict__ rand32,
-                u32* __restrict__ out, long n, int mode) {
+                u32* __restrict__ out, long n) {
     extern __shared__ __align__(128) u32 sm[];          // 2 x kChunkWords
     __shared__ __align__(8) unsigned long long full[2];
     const int tid = threadIdx.x;
@@ -199,19 +159,59 @@ k_pedersen_hash(PedersenDev P, const u32* __restrict__ consts, const u32* __rest
             __syncthreads();                            // every thread is done with buffer b
             if (tid == 0 && c + 2 < total) issue(c + 2, b);
         }
-        // projective -> affine (crh/pedersen/mod.rs:128 `result.into()`)
-        u32 z[8], zi[8], x[8], y[8];
-        if (active) fp_copy(z, acc.Z); else fp_one<F>(z);
-        warp_batch_inverse<F>(zi, z, pm);
+        // projective result; k_pedersen_normalise turns it into the affine output (crh/pedersen/mod.rs:128 `result.into()`)
         if (active) {
-            fp_mul<F>(x, acc.X, zi, pm);
-            if (mode == 0) {
-                fp_mul<F>(y, acc.Y, zi, pm);
-                st_elem(out + 16 * i, x);
-                st_elem(out + 16 * i + 8, y);
-            } else {
-                st_elem(out + 8 * i, x);
-            }
+            u32* o = out + 32 * i;
+            st_elem(o, acc.X);
+            st_elem(o + 8, acc.Y);
+            st_elem(o + 16, acc.Z);
+        }
+    }
+}
+
+// Projective -> affine for n points with one field inversion per 32 points (Montgomery's trick along a
+// thread's own sequence of points: prefix products, one Fermat inversion, back-substitution).  A warp
+// pays for an inversion once whether its lanes invert the same or different values, so batching has to
+// be sequential inside a thread; thread t owns points t, t + stride, t + 2*stride, ... (coalesced).
+// proj: n x (X, Y, Z, scratch) of 8 words; mode 0: out = n x (x, y), mode 1: out = n x x.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_pedersen_normalise(const u32* __restrict__ consts, u32* __restrict__ proj, u32* __restrict__ out, long n, int mode, int zero) {
+    constexpr int B = 32;
+    const long stride = (n + B - 1) / B;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= stride) return;
+    u32 pm[8], acc[8], z[8], tmp[8];
+    ld_elem(pm, consts + (int)threadIdx.x * zero);
+    fp_one<F>(acc);
+#pragma unroll 1
+    for (int j = 0; j < B; j++) {
+        const long i = t + j * stride;
+        if (i >= n) break;
+        st_elem(proj + 32 * i + 24, acc);              // prefix product of the Z's before this one
+        ld_elem(z, proj + 32 * i + 16);
+        fp_mul<F>(acc, acc, z, pm);
+    }
+    u32 inv[8];
+    fp_inv<F>(inv, acc, pm);
+#pragma unroll 1
+    for (int j = B - 1; j >= 0; j--) {
+        const long i = t + j * stride;
+        if (i >= n) continue;
+        u32 zi[8], c[8];
+        ld_elem(tmp, proj + 32 * i + 24);
+        fp_mul<F>(zi, inv, tmp, pm);                   // 1 / Z_i
+        ld_elem(z, proj + 32 * i + 16);
+        fp_mul<F>(inv, inv, z, pm);
+        ld_elem(c, proj + 32 * i);
+        fp_mul<F>(c, c, zi, pm);
+        if (mode == 0) {
+            st_elem(out + 16 * i, c);
+            ld_elem(c, proj + 32 * i + 8);
+            fp_mul<F>(c, c, zi, pm);
+            st_elem(out + 16 * i + 8, c);
+        } else {
+            st_elem(out + 8 * i, c);
         }
     }
 }
@@ -285,9 +285,18 @@ cpb_status launch_hash_f(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, siz
     size_t smem = 2 * (size_t)kChunkBytes;
     int grid = 1;
     CPB_TRY(ped_grid(k_pedersen_hash<F>, smem, c->sms, (long)n, grid));
+    u32* proj = nullptr;
+    CPB_CUDA(cudaMallocAsync((void**)&proj, n * 128, st));           // stream-ordered scratch: n x (X, Y, Z, prefix)
     k_pedersen_hash<F><<<grid, kPedBlock, smem, st>>>(c->dev, c->d_consts, c->d_table, in, (long)len, (long)stride, rand32,
-                                                      out, (long)n, mode);
-    CPB_CUDA(cudaGetLastError());
+                                                      proj, (long)n);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        long threads = ((long)n + 31) / 32;
+        k_pedersen_normalise<F><<<(int)((threads + 127) / 128), 128, 0, st>>>(c->d_consts, proj, out, (long)n, mode, 0);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(proj, st);
+    if (e != cudaSuccess) return fail(CPB_CUDA_ERROR, "pedersen launch failed: %s", cudaGetErrorString(e));
     return CPB_OK;
 }
 
