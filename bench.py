@@ -127,6 +127,17 @@ def synthetic_leaves_torch(torch, n, leaf_len, modulus, seed, device, pin=False)
     return x.to(device) if device is not None else x
 
 
+def merkle_launches(n: int) -> int:
+    """Kernel launches of one cpb_merkle_poseidon_build_dev over n leaves (csrc/cpb_poseidon.cu: merkle_build_streams):
+    S subtrees on S streams (leaf hash + their levels each), then the top log2 S levels."""
+    h = n.bit_length() - 1
+    S = 8
+    while S > 1 and n // S < (1 << 14):
+        S >>= 1
+    lg = S.bit_length() - 1
+    return S * (1 + (h - lg)) + lg if S > 1 else 1 + h
+
+
 # --------------------------------------------------------------------------------- CPU baseline
 def cpu_baseline(field_key, leaf_len, threads, log_sample):
     """C restatement of the reference CPU path (kind "port") on a bounded sample: a 2^log_sample-leaf tree."""
@@ -279,12 +290,16 @@ def run_b200(args):
     peaks = measured_peaks()
     peak = peaks["hbm_gbs"] if peaks else HBM_PEAK_FALLBACK
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # DRAM traffic of this kernel from the committed ncu --set full capture (profiles/r1_ncu_crh_*.txt: 2^20-hash launch,
+    # dram__bytes_read.sum + dram__bytes_write.sum), scaled per hash to this launch
+    ncu_bytes_per_hash = {"bn254": (67.304192e6 + 9.151744e6) / (1 << 20), "bls": (67.3e6 + 9.6e6) / (1 << 20)}[field_key]
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_bytes_per_hash * n_local, "traffic_source": "ncu capture of a 2^20-hash launch, scaled per hash",
                 "kernel": "k_poseidon_crh (leaf level: %d hashes of %d elements)" % (n_local, leaf_len), "kernel_ms": k_ms,
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)",
                 "note": "the path is bound by the integer multiply pipe, not HBM (~6e4 IMAD-class instructions per 96 algorithmic bytes); see integer_pipe"}
     # integer-pipe view: wide 32x32->64 multiply-adds needed by the schedule vs the measured issue rate
-    wide_per_perm = {"bn254": 61896 + 8 * 65 * 0, "bls": 59900}[field_key]
+    wide_per_perm = {"bn254": 61896, "bls": 44784}[field_key]           # DESIGN.md §4.2; matches the ncu opcode mix
     sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
     int_peak = 148 * 32 * sm_clock * 1e6                                # IMAD.WIDE/IMAD.HI: 32 lanes/clk/SM (tools/ubench_int.cu, ncu)
     integer = {"wide_madds_per_perm": wide_per_perm, "achieved_wide_madds_per_s": n_local * wide_per_perm / (k_ms * 1e-3),
@@ -292,8 +307,7 @@ def run_b200(args):
                "peak_source": "148 SMs x 32 lanes/clk (measured IMAD.WIDE rate) x sampled SM clock"}
 
     if rank == 0:
-        levels_local = (n_local.bit_length() - 1)
-        launches_per_step = 1 + levels_local + ((world.bit_length() - 1) if world > 1 else 0)
+        launches_per_step = merkle_launches(n_local) + ((world.bit_length() - 1) if world > 1 else 0)
         threads = os.cpu_count() or 1
         cpu_v, cpu_dt, cpu_perms = cpu_baseline(field_key, leaf_len, threads, min(logn, 18))
         line = {"metric": "poseidon_perms_per_sec", "value": value, "unit": "perms/s", "n_gpus": world, "steps": args.steps,

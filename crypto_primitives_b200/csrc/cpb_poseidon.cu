@@ -113,9 +113,16 @@ PoseidonDev to_dev(const host::PoseidonSchedule& S) {
         case CPB_BLS12_377_FR: CPB_FOR_T(Bls12_377_Fr, M, __VA_ARGS__)               \
     }
 
-cpb_status launch_crh(cpb_poseidon_ctx* c, const u32* in, size_t len, u32* out, size_t n, cudaStream_t st) {
+cpb_status launch_crh(cpb_poseidon_ctx* c, const u32* in, size_t len, u32* out, size_t n, cudaStream_t st, size_t n_out = 1) {
+    if (n == 0 || n_out == 0) return CPB_OK;
+    CPB_FOR_FIELD(launch_crh_ft, c, in, len, out, n_out, n, st)
+    return fail(CPB_UNSUPPORTED, "state width t=%d is not built (this library: t = 2..9)", c->dev.t);
+}
+cpb_status launch_verify(cpb_poseidon_ctx* c, cpb_poseidon_ctx* node, const u32* root, const u32* leaves, size_t leaf_len,
+                         const u32* siblings, const u32* paths, int plen, const unsigned long long* indexes, unsigned char* ok,
+                         size_t n, cudaStream_t st) {
     if (n == 0) return CPB_OK;
-    CPB_FOR_FIELD(launch_crh_ft, c, in, len, out, n, st)
+    CPB_FOR_FIELD(launch_verify_ft, c, node, root, leaves, leaf_len, siblings, paths, plen, indexes, ok, n, st)
     return fail(CPB_UNSUPPORTED, "state width t=%d is not built (this library: t = 2..9)", c->dev.t);
 }
 cpb_status launch_permute(cpb_poseidon_ctx* c, const u32* in, u32* out, size_t n, cudaStream_t st) {
@@ -380,6 +387,26 @@ cpb_status cpb_poseidon_crh_batch_dev(cpb_poseidon_ctx* c, const uint64_t* in, s
     DeviceGuard g(c->device);
     return launch_crh(c, (const u32*)in, len, (u32*)out, n, (cudaStream_t)stream);
 }
+cpb_status cpb_poseidon_sponge_batch_dev(cpb_poseidon_ctx* c, const uint64_t* in, size_t len, uint64_t* out, size_t n_squeeze,
+                                         size_t n, void* stream) {
+    CPB_TRY(check_ctx(c));
+    DeviceGuard g(c->device);
+    return launch_crh(c, (const u32*)in, len, (u32*)out, n, (cudaStream_t)stream, n_squeeze);
+}
+cpb_status cpb_merkle_poseidon_verify_batch_dev(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, const uint64_t* root,
+                                                const uint64_t* leaves, size_t leaf_len, const uint64_t* leaf_sibling_hashes,
+                                                const uint64_t* auth_paths, size_t path_len, const uint64_t* leaf_indexes,
+                                                uint8_t* ok, size_t n, void* stream) {
+    CPB_TRY(check_ctx(leaf));
+    CPB_TRY(check_ctx(node));
+    if (leaf->device != node->device || leaf->field_id != node->field_id || leaf->dev.t != node->dev.t)
+        return fail(CPB_UNSUPPORTED, "leaf and node contexts must share device, field and state width");
+    if (node->dev.rate < 2) return fail(CPB_UNSUPPORTED, "two-to-one with rate < 2 not supported");
+    if (path_len > 62) return fail(CPB_BAD_PARAMS, "path too long");
+    DeviceGuard g(leaf->device);
+    return launch_verify(leaf, node, (const u32*)root, (const u32*)leaves, leaf_len, (const u32*)leaf_sibling_hashes,
+                         (const u32*)auth_paths, (int)path_len, (const unsigned long long*)leaf_indexes, ok, n, (cudaStream_t)stream);
+}
 cpb_status cpb_poseidon_compress_batch_dev(cpb_poseidon_ctx* c, const uint64_t* pairs, uint64_t* out, size_t n, void* stream) {
     CPB_TRY(check_ctx(c));
     if (c->dev.rate < 2)   // two absorbs then one squeeze = one permutation only when rate >= 2
@@ -433,6 +460,52 @@ cpb_status cpb_poseidon_permute_batch(cpb_poseidon_ctx* c, const uint64_t* in, u
 }
 cpb_status cpb_poseidon_crh_batch(cpb_poseidon_ctx* c, const uint64_t* in, size_t len, uint64_t* out, size_t n) {
     return host_roundtrip_crh(c, in, len, len, out, 1, n, 0);
+}
+cpb_status cpb_poseidon_sponge_batch(cpb_poseidon_ctx* c, const uint64_t* in, size_t len, uint64_t* out, size_t n_squeeze, size_t n) {
+    CPB_TRY(check_ctx(c));
+    if (n == 0 || n_squeeze == 0) return CPB_OK;
+    if ((!in && len) || !out) return fail(CPB_NULL_POINTER, "null buffer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    size_t in_b = n * len * 32, out_b = n * n_squeeze * 32;
+    CPB_TRY(c->s_in.reserve(in_b ? in_b : 32));
+    CPB_TRY(c->s_out.reserve(out_b));
+    if (in_b) CPB_CUDA(cudaMemcpyAsync(c->s_in.ptr, in, in_b, cudaMemcpyHostToDevice, c->stream));
+    CPB_TRY(launch_crh(c, (const u32*)c->s_in.ptr, len, (u32*)c->s_out.ptr, n, c->stream, n_squeeze));
+    CPB_CUDA(cudaMemcpyAsync(out, c->s_out.ptr, out_b, cudaMemcpyDeviceToHost, c->stream));
+    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    return CPB_OK;
+}
+cpb_status cpb_merkle_poseidon_verify_batch(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, const uint64_t* root,
+                                            const uint64_t* leaves, size_t leaf_len, const uint64_t* leaf_sibling_hashes,
+                                            const uint64_t* auth_paths, size_t path_len, const uint64_t* leaf_indexes, uint8_t* ok,
+                                            size_t n) {
+    CPB_TRY(check_ctx(leaf));
+    CPB_TRY(check_ctx(node));
+    if (n == 0) return CPB_OK;
+    if (!root || (!leaves && leaf_len) || !leaf_sibling_hashes || (!auth_paths && path_len) || !leaf_indexes || !ok)
+        return fail(CPB_NULL_POINTER, "null buffer");
+    std::lock_guard<std::mutex> lk(leaf->mu);
+    DeviceGuard g(leaf->device);
+    size_t b_root = 32, b_leaves = n * leaf_len * 32, b_sib = n * 32, b_path = n * path_len * 32, b_idx = n * 8;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o_leaves = up(b_root), o_sib = o_leaves + up(b_leaves), o_path = o_sib + up(b_sib), o_idx = o_path + up(b_path),
+           total = o_idx + up(b_idx);
+    CPB_TRY(leaf->s_in.reserve(total));
+    CPB_TRY(leaf->s_out.reserve(n));
+    char* d = (char*)leaf->s_in.ptr;
+    cudaStream_t st = leaf->stream;
+    CPB_CUDA(cudaMemcpyAsync(d, root, b_root, cudaMemcpyHostToDevice, st));
+    if (b_leaves) CPB_CUDA(cudaMemcpyAsync(d + o_leaves, leaves, b_leaves, cudaMemcpyHostToDevice, st));
+    CPB_CUDA(cudaMemcpyAsync(d + o_sib, leaf_sibling_hashes, b_sib, cudaMemcpyHostToDevice, st));
+    if (b_path) CPB_CUDA(cudaMemcpyAsync(d + o_path, auth_paths, b_path, cudaMemcpyHostToDevice, st));
+    CPB_CUDA(cudaMemcpyAsync(d + o_idx, leaf_indexes, b_idx, cudaMemcpyHostToDevice, st));
+    CPB_TRY(cpb_merkle_poseidon_verify_batch_dev(leaf, node, (const uint64_t*)d, (const uint64_t*)(d + o_leaves), leaf_len,
+                                                 (const uint64_t*)(d + o_sib), (const uint64_t*)(d + o_path), path_len,
+                                                 (const uint64_t*)(d + o_idx), (uint8_t*)leaf->s_out.ptr, n, st));
+    CPB_CUDA(cudaMemcpyAsync(ok, leaf->s_out.ptr, n, cudaMemcpyDeviceToHost, st));
+    CPB_CUDA(cudaStreamSynchronize(st));
+    return CPB_OK;
 }
 cpb_status cpb_poseidon_compress_batch(cpb_poseidon_ctx* c, const uint64_t* pairs, uint64_t* out, size_t n) {
     CPB_TRY(check_ctx(c));

@@ -148,34 +148,79 @@ template <class F, int T> CPB_HD void pos_permute(u32 (&s)[T][8], const Poseidon
     }
 }
 
-// CRH::evaluate over `len` elements at `in` (contiguous, 32 B each) -> out (8 limbs).
-// Absorb semantics of mod.rs:124-153: fill `rate` lanes, permute while more input remains;
-// the squeeze then permutes once (so an empty input still costs one permutation).
-template <class F, int T> CPB_HD void pos_crh(u32* out, const u32* in, long len, const PoseidonDev& P, const u32* cs, const u32* pm) {
+// New sponge -> absorb `len` elements at `in` -> squeeze `n_out` native elements to `out` (8 limbs each).
+// n_out == 1 is crh::poseidon::CRH::evaluate (R/crh/poseidon/mod.rs:30-40).  Absorb semantics of
+// R/sponge/poseidon/mod.rs:124-153: fill `rate` lanes, permute while more input remains; the squeeze
+// (mod.rs:156-186, 323-345) permutes once from Absorbing mode (so an empty input still costs one
+// permutation), then emits `rate` lanes per permutation.
+template <class F, int T>
+CPB_HD void pos_sponge(u32* out, long n_out, const u32* in, long len, const PoseidonDev& P, const u32* cs, const u32* pm) {
     u32 s[T][8];
 #pragma unroll
     for (int i = 0; i < T; i++) fp_zero(s[i]);
     const int rate = P.rate, cap = P.cap;
     const long nblocks = len <= rate ? 1 : (len + rate - 1) / rate;
+    const long nsq = n_out <= rate ? 1 : (n_out + rate - 1) / rate;
 #pragma unroll 1
-    for (long b = 0; b < nblocks; b++) {
-        const long pos = b * rate;
-        const long rem = len - pos;
-        const int cnt = rem > rate ? rate : (int)rem;
+    for (long b = 0; b < nblocks + nsq - 1; b++) {
+        if (b < nblocks) {
+            const long pos = b * rate;
+            const long rem = len - pos;
+            const int cnt = rem > rate ? rate : (int)rem;
 #pragma unroll
-        for (int i = 0; i < T; i++) {
-            int lane = i - cap;
-            if (lane >= 0 && lane < cnt) {
-                u32 e[8];
-                ld_elem(e, in + 8 * (pos + lane));
-                fp_add<F>(s[i], s[i], e);
+            for (int i = 0; i < T; i++) {
+                int lane = i - cap;
+                if (lane >= 0 && lane < cnt) {
+                    u32 e[8];
+                    ld_elem(e, in + 8 * (pos + lane));
+                    fp_add<F>(s[i], s[i], e);
+                }
             }
         }
         pos_permute<F, T>(s, P, cs, pm);
-    }
+        if (b >= nblocks - 1) {
+            const long q = b - (nblocks - 1);          // squeeze block index
+            const long left = n_out - q * rate;
+            const int cnt = left > rate ? rate : (int)left;
 #pragma unroll
-    for (int i = 0; i < T; i++)
-        if (i == cap) fp_copy(out, s[i]);
+            for (int i = 0; i < T; i++) {
+                int lane = i - cap;
+                if (lane >= 0 && lane < cnt) st_elem(out + 8 * (q * rate + lane), s[i]);
+            }
+        }
+    }
+}
+
+template <class F, int T> CPB_HD void pos_crh(u32* out, const u32* in, long len, const PoseidonDev& P, const u32* cs, const u32* pm) {
+    pos_sponge<F, T>(out, 1, in, len, P, cs, pm);
+}
+
+// Path::verify (R/merkle_tree/mod.rs:172-212) for the field-leaf Config: hash the leaf, fold the
+// authentication path bottom-up choosing sides by the index bits, compare with the root.
+// auth_path: plen elements ordered root side first (as Path.auth_path).  PL/PN, cl/cn: leaf / node schedules.
+template <class F, int T>
+CPB_HD bool pos_verify_path(const u32* leaf, long leaf_len, const u32* sibling, const u32* auth_path, int plen, unsigned long long index,
+                            const u32* root, const PoseidonDev& PL, const u32* cl, const PoseidonDev& PN, const u32* cn, const u32* pm) {
+    alignas(16) u32 pair[16];        // read back through 128-bit loads
+    u32 cur[8];
+    pos_crh<F, T>(cur, leaf, leaf_len, PL, cl, pm);
+    u32 sib[8];
+    ld_elem(sib, sibling);
+#pragma unroll 1
+    for (int level = plen; level >= 0; level--) {
+        const bool right = (index & 1ull) != 0;       // computed node is the right child
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            pair[j] = right ? sib[j] : cur[j];
+            pair[8 + j] = right ? cur[j] : sib[j];
+        }
+        pos_crh<F, T>(cur, pair, 2, PN, cn, pm);
+        index >>= 1;
+        if (level > 0) ld_elem(sib, auth_path + 8 * (level - 1));
+    }
+    u32 r[8];
+    ld_elem(r, root);
+    return fp_eq(cur, r);
 }
 
 }  // namespace cpb

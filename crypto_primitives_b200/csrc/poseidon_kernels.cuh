@@ -17,7 +17,7 @@ constexpr int pos_min_blocks(int t) { return t <= 3 ? 5 : t <= 5 ? 3 : 1; }
 template <class F, int T>
 __global__ void __launch_bounds__(kBlock, pos_min_blocks(T))
 k_poseidon_crh(PoseidonDev P, const u32* __restrict__ consts, const u32* __restrict__ in, u32* __restrict__ out,
-               long n, long len) {
+               long n, long len, long n_out) {
     extern __shared__ __align__(16) u32 cs[];
     __shared__ __align__(8) unsigned long long mbar;
     tma_stage_to_smem(cs, consts, (unsigned)P.n_elems * 32u, &mbar);
@@ -26,9 +26,7 @@ k_poseidon_crh(PoseidonDev P, const u32* __restrict__ consts, const u32* __restr
     ld_elem(pm, ct + 8 * P.off_mod);
     const long stride = (long)gridDim.x * blockDim.x;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        u32 r[8];
-        pos_crh<F, T>(r, in + 8 * len * i, len, P, ct, pm);
-        st_elem(out + 8 * i, r);
+        pos_sponge<F, T>(out + 8 * n_out * i, n_out, in + 8 * len * i, len, P, ct, pm);
     }
 }
 
@@ -93,11 +91,11 @@ template <class K> cpb_status grid_for(K kernel, size_t smem, int sms, long n, i
 }
 
 template <class F, int T>
-cpb_status launch_crh_ft(cpb_poseidon_ctx* c, const u32* in, size_t len, u32* out, size_t n, cudaStream_t st) {
+cpb_status launch_crh_ft(cpb_poseidon_ctx* c, const u32* in, size_t len, u32* out, size_t n_out, size_t n, cudaStream_t st) {
     size_t smem = (size_t)c->dev.n_elems * 32;
     int grid = 1;
     CPB_TRY(grid_for(k_poseidon_crh<F, T>, smem, c->sms, (long)n, grid));
-    k_poseidon_crh<F, T><<<grid, kBlock, smem, st>>>(c->dev, c->d_consts, in, out, (long)n, (long)len);
+    k_poseidon_crh<F, T><<<grid, kBlock, smem, st>>>(c->dev, c->d_consts, in, out, (long)n, (long)len, (long)n_out);
     CPB_CUDA(cudaGetLastError());
     return CPB_OK;
 }
@@ -112,13 +110,52 @@ cpb_status launch_permute_ft(cpb_poseidon_ctx* c, const u32* in, u32* out, size_
 }
 
 
+// One Path::verify per thread; both round schedules staged in shared memory.
+template <class F, int T>
+__global__ void __launch_bounds__(kBlock, pos_min_blocks(T))
+k_poseidon_verify_paths(PoseidonDev PL, const u32* __restrict__ consts_l, PoseidonDev PN, const u32* __restrict__ consts_n,
+                        const u32* __restrict__ root, const u32* __restrict__ leaves, long leaf_len,
+                        const u32* __restrict__ siblings, const u32* __restrict__ paths, int plen,
+                        const unsigned long long* __restrict__ indexes, unsigned char* __restrict__ ok, long n) {
+    extern __shared__ __align__(16) u32 cs[];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    u32* csn = cs + 8 * PL.n_elems;
+    tma_stage_to_smem(cs, consts_l, (unsigned)PL.n_elems * 32u, &mbar[0]);
+    tma_stage_to_smem(csn, consts_n, (unsigned)PN.n_elems * 32u, &mbar[1]);
+    const int z = (int)threadIdx.x * PL.zero;
+    u32 pm[8];
+    ld_elem(pm, cs + z + 8 * PL.off_mod);
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        ok[i] = pos_verify_path<F, T>(leaves + 8 * leaf_len * i, leaf_len, siblings + 8 * i, paths + 8 * (long)plen * i, plen, indexes[i],
+                                      root, PL, cs + z, PN, csn + z, pm) ? 1 : 0;
+}
+
+template <class F, int T>
+cpb_status launch_verify_ft(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, const u32* root, const u32* leaves, size_t leaf_len,
+                            const u32* siblings, const u32* paths, int plen, const unsigned long long* indexes,
+                            unsigned char* ok, size_t n, cudaStream_t st) {
+    size_t smem = ((size_t)leaf->dev.n_elems + node->dev.n_elems) * 32;
+    if (smem > 200 * 1024) return fail(CPB_UNSUPPORTED, "round schedules (%zu B) exceed shared memory", smem);
+    int grid = 1;
+    CPB_TRY(grid_for(k_poseidon_verify_paths<F, T>, smem, leaf->sms, (long)n, grid));
+    k_poseidon_verify_paths<F, T><<<grid, kBlock, smem, st>>>(leaf->dev, leaf->d_consts, node->dev, node->d_consts, root, leaves,
+                                                              (long)leaf_len, siblings, paths, plen, indexes, ok, (long)n);
+    CPB_CUDA(cudaGetLastError());
+    return CPB_OK;
+}
+
 // explicit instantiations live in poseidon_inst_<field>.cu
 #define CPB_POS_WIDTHS(M, F) M(F, 2) M(F, 3) M(F, 4) M(F, 5) M(F, 6) M(F, 7) M(F, 8) M(F, 9)
 #define CPB_POS_INSTANTIATE(F, T)                                                                                        \
-    template cpb_status launch_crh_ft<F, T>(cpb_poseidon_ctx*, const u32*, size_t, u32*, size_t, cudaStream_t);            \
-    template cpb_status launch_permute_ft<F, T>(cpb_poseidon_ctx*, const u32*, u32*, size_t, cudaStream_t);
+    template cpb_status launch_crh_ft<F, T>(cpb_poseidon_ctx*, const u32*, size_t, u32*, size_t, size_t, cudaStream_t);            \
+    template cpb_status launch_permute_ft<F, T>(cpb_poseidon_ctx*, const u32*, u32*, size_t, cudaStream_t);             \
+    template cpb_status launch_verify_ft<F, T>(cpb_poseidon_ctx*, cpb_poseidon_ctx*, const u32*, const u32*, size_t, const u32*, \
+                                               const u32*, int, const unsigned long long*, unsigned char*, size_t, cudaStream_t);
 #define CPB_POS_EXTERN(F, T)                                                                                             \
-    extern template cpb_status launch_crh_ft<F, T>(cpb_poseidon_ctx*, const u32*, size_t, u32*, size_t, cudaStream_t);     \
-    extern template cpb_status launch_permute_ft<F, T>(cpb_poseidon_ctx*, const u32*, u32*, size_t, cudaStream_t);
+    extern template cpb_status launch_crh_ft<F, T>(cpb_poseidon_ctx*, const u32*, size_t, u32*, size_t, size_t, cudaStream_t);     \
+    extern template cpb_status launch_permute_ft<F, T>(cpb_poseidon_ctx*, const u32*, u32*, size_t, cudaStream_t);      \
+    extern template cpb_status launch_verify_ft<F, T>(cpb_poseidon_ctx*, cpb_poseidon_ctx*, const u32*, const u32*, size_t, const u32*, \
+                                                      const u32*, int, const unsigned long long*, unsigned char*, size_t, cudaStream_t);
 
 }  // namespace cpb

@@ -323,6 +323,26 @@ class MerkleTree:
             prev = path
         return MultiPath(sibs, prefix, suffixes, idx)
 
+    def verify_proofs_batch(self, proofs, leaves, root_hash=None) -> np.ndarray:
+        """Many Path::verify (mod.rs:172-212) in one kernel launch (field-leaf Config): proofs = list of Path for
+        `leaves[i]`; returns a bool array.  One GPU thread recomputes one root."""
+        if not isinstance(self.config, PoseidonFieldConfig):
+            raise NotImplementedError("batched verification is implemented for the Poseidon field-leaf Config")
+        n = len(proofs)
+        lv = np.ascontiguousarray(leaves, dtype=np.uint64)
+        assert lv.shape[0] == n and lv.ndim == 3
+        plen = self._height - 2
+        sib = np.ascontiguousarray(np.stack([p.leaf_sibling_hash for p in proofs]), dtype=np.uint64)
+        paths = np.ascontiguousarray(np.stack([np.stack(p.auth_path) if plen else np.zeros((0, 4), dtype=np.uint64) for p in proofs]),
+                                     dtype=np.uint64).reshape(n, plen, 4)
+        idx = np.array([p.leaf_index for p in proofs], dtype=np.uint64)
+        root = np.ascontiguousarray(self.root() if root_hash is None else root_hash, dtype=np.uint64)
+        ok = np.zeros(n, dtype=np.uint8)
+        N.check(N.lib.cpb_merkle_poseidon_verify_batch(self.leaf_hash_param.context(self.device), self.two_to_one_hash_param.context(self.device),
+                                                       _p(root), _p(lv), lv.shape[1], _p(sib), _p(paths), plen, _p(idx),
+                                                       ok.ctypes.data_as(N.u8p), n))
+        return ok.astype(bool)
+
     def _updated_path(self, index: int, new_leaf):
         """mod.rs:627-677."""
         cfg, dev = self.config, self.device

@@ -96,3 +96,125 @@ def get_default_poseidon_parameters(field: Field, rate: int, optimized_for_weigh
         return None
     ark, mds = find_poseidon_ark_and_mds(field, field.modulus_bit_size, rate, rf.value, rp.value, skip.value)
     return PoseidonConfig(field, rf.value, rp.value, alpha.value, mds, ark, rate, 1)
+
+
+class PoseidonSponge:
+    """Duplex sponge over the GPU permutation -- host mirror of PoseidonSponge<F> (R/sponge/poseidon/mod.rs:47-63):
+    CryptographicSponge::{new, absorb, squeeze_bytes, squeeze_bits, squeeze_field_elements} (mod.rs:220-321) and
+    FieldBasedCryptographicSponge::squeeze_native_field_elements (mod.rs:323-345), with the same mode bookkeeping
+    (absorb_internal / squeeze_internal, mod.rs:124-186).  Only native field elements can be absorbed (the `Fp` and
+    `&[Fp]` Absorb impls, R/sponge/absorb.rs:154-167, 284-292).  Every permutation is one GPU call of batch size 1:
+    correct but slow -- a single transcript is sequential by nature; for many independent sponges use
+    `absorb_squeeze_batch`."""
+
+    def __init__(self, parameters: PoseidonConfig, device: int = 0):
+        self.parameters = parameters
+        self.device = device
+        t = parameters.rate + parameters.capacity
+        self.state = np.zeros((t, 4), dtype=np.uint64)
+        self.mode = ("Absorbing", 0)            # DuplexSpongeMode::{Absorbing{next_absorb_index}, Squeezing{next_squeeze_index}}
+
+    @classmethod
+    def new(cls, parameters: PoseidonConfig, device: int = 0):
+        return cls(parameters, device)
+
+    # -- internals
+    def _permute(self):
+        out = np.empty_like(self.state)
+        N.check(N.lib.cpb_poseidon_permute_batch(self.parameters.context(self.device), self.state.ctypes.data_as(N.u64p),
+                                                 out.ctypes.data_as(N.u64p), 1))
+        self.state = out
+
+    def _add(self, lane: int, elem: np.ndarray):
+        f = self.parameters.field
+        a, b = f.to_ints(self.state[lane])[0], f.to_ints(elem)[0]
+        self.state[lane] = f.elements([(a + b) % f.modulus])[0]
+
+    def _absorb_internal(self, rate_start: int, elems: np.ndarray):           # mod.rs:124-153
+        c = self.parameters
+        rem = elems
+        while True:
+            if rate_start + len(rem) <= c.rate:
+                for i, e in enumerate(rem):
+                    self._add(c.capacity + i + rate_start, e)
+                self.mode = ("Absorbing", rate_start + len(rem))
+                return
+            k = c.rate - rate_start
+            for i, e in enumerate(rem[:k]):
+                self._add(c.capacity + i + rate_start, e)
+            self._permute()
+            rem = rem[k:]
+            rate_start = 0
+
+    def _squeeze_internal(self, rate_start: int, n_out: int) -> np.ndarray:  # mod.rs:156-186
+        c = self.parameters
+        out = []
+        rem = n_out
+        while True:
+            if rate_start + rem <= c.rate:
+                out.extend(self.state[c.capacity + rate_start: c.capacity + rate_start + rem])
+                self.mode = ("Squeezing", rate_start + rem)
+                return np.array(out, dtype=np.uint64).reshape(-1, 4)
+            k = c.rate - rate_start
+            out.extend(self.state[c.capacity + rate_start: c.capacity + rate_start + k])
+            rem -= k
+            if rem != 0:
+                self._permute()
+            rate_start = 0
+
+    # -- public surface
+    def absorb(self, elems):
+        """elems: (k, 4) Montgomery limbs (or a single (4,) element)."""
+        e = np.asarray(elems, dtype=np.uint64).reshape(-1, 4)
+        if e.shape[0] == 0:
+            return
+        kind, idx = self.mode
+        if kind == "Absorbing":
+            if idx == self.parameters.rate:
+                self._permute()
+                idx = 0
+            self._absorb_internal(idx, e)
+        else:
+            self._absorb_internal(0, e)
+
+    def squeeze_native_field_elements(self, num_elements: int) -> np.ndarray:
+        kind, idx = self.mode
+        if kind == "Absorbing":
+            self._permute()
+            return self._squeeze_internal(0, num_elements)
+        if idx == self.parameters.rate:
+            self._permute()
+            idx = 0
+        return self._squeeze_internal(idx, num_elements)
+
+    squeeze_field_elements = squeeze_native_field_elements       # the native TypeId fast path, mod.rs:309-315
+
+    def squeeze_bytes(self, num_bytes: int) -> bytes:
+        """mod.rs:259-274."""
+        f = self.parameters.field
+        usable = (f.modulus_bit_size - 1) // 8
+        n = (num_bytes + usable - 1) // usable
+        out = b"".join(v.to_bytes(32, "little")[:usable] for v in f.to_ints(self.squeeze_native_field_elements(n)))
+        return out[:num_bytes]
+
+    def squeeze_bits(self, num_bits: int) -> list:
+        """mod.rs:276-291."""
+        f = self.parameters.field
+        usable = f.modulus_bit_size - 1
+        n = (num_bits + usable - 1) // usable
+        bits = []
+        for v in f.to_ints(self.squeeze_native_field_elements(n)):
+            bits.extend(bool((v >> i) & 1) for i in range(usable))
+        return bits[:num_bits]
+
+
+def absorb_squeeze_batch(parameters: PoseidonConfig, inputs, num_squeeze: int, device: int = 0) -> np.ndarray:
+    """n independent sponges in one kernel launch: new -> absorb(inputs[i]) -> squeeze_native_field_elements(num_squeeze).
+    inputs (n, len, 4) -> (n, num_squeeze, 4)."""
+    inp = np.ascontiguousarray(inputs, dtype=np.uint64)
+    assert inp.ndim == 3 and inp.shape[2] == 4
+    n, ln = inp.shape[0], inp.shape[1]
+    out = np.empty((n, num_squeeze, 4), dtype=np.uint64)
+    N.check(N.lib.cpb_poseidon_sponge_batch(parameters.context(device), inp.ctypes.data_as(N.u64p), ln, out.ctypes.data_as(N.u64p),
+                                            num_squeeze, n))
+    return out

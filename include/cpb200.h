@@ -112,6 +112,12 @@ cpb_status cpb_poseidon_crh_batch(cpb_poseidon_ctx* ctx, const uint64_t* in, siz
 cpb_status cpb_poseidon_crh_batch_dev(cpb_poseidon_ctx* ctx, const uint64_t* in, size_t len, uint64_t* out, size_t n,
                                       void* stream);
 
+/* n independent sponges: PoseidonSponge::new -> absorb(len native elements) -> squeeze_native_field_elements(n_squeeze)
+ * (R/sponge/poseidon/mod.rs:220-257, 323-345); out: n x n_squeeze elements.  n_squeeze = 1 is the CRH. */
+cpb_status cpb_poseidon_sponge_batch(cpb_poseidon_ctx* ctx, const uint64_t* in, size_t len, uint64_t* out, size_t n_squeeze, size_t n);
+cpb_status cpb_poseidon_sponge_batch_dev(cpb_poseidon_ctx* ctx, const uint64_t* in, size_t len, uint64_t* out, size_t n_squeeze,
+                                         size_t n, void* stream);
+
 /* n x crh::poseidon::TwoToOneCRH::compress / evaluate (mod.rs:58-79): pairs[i] = (left, right). */
 cpb_status cpb_poseidon_compress_batch(cpb_poseidon_ctx* ctx, const uint64_t* pairs, uint64_t* out, size_t n);
 cpb_status cpb_poseidon_compress_batch_dev(cpb_poseidon_ctx* ctx, const uint64_t* pairs, uint64_t* out, size_t n,
@@ -133,6 +139,18 @@ cpb_status cpb_merkle_poseidon_from_digests(cpb_poseidon_ctx* node_ctx, const ui
                                             uint64_t* non_leaf_nodes);
 cpb_status cpb_merkle_poseidon_from_digests_dev(cpb_poseidon_ctx* node_ctx, const uint64_t* leaf_digests, size_t n,
                                                 uint64_t* non_leaf_nodes, void* stream);
+
+/* n x Path::verify (R/merkle_tree/mod.rs:172-212) for the field-leaf Config against one root: path i is
+ * (leaf_sibling_hashes[i], auth_paths[i*path_len .. (i+1)*path_len) ordered root side first as Path.auth_path,
+ * leaf_indexes[i]); ok[i] = 1 when the recomputed root matches.  Tree height = path_len + 2. */
+cpb_status cpb_merkle_poseidon_verify_batch(cpb_poseidon_ctx* leaf_ctx, cpb_poseidon_ctx* node_ctx, const uint64_t* root,
+                                            const uint64_t* leaves, size_t leaf_len, const uint64_t* leaf_sibling_hashes,
+                                            const uint64_t* auth_paths, size_t path_len, const uint64_t* leaf_indexes, uint8_t* ok,
+                                            size_t n);
+cpb_status cpb_merkle_poseidon_verify_batch_dev(cpb_poseidon_ctx* leaf_ctx, cpb_poseidon_ctx* node_ctx, const uint64_t* root,
+                                                const uint64_t* leaves, size_t leaf_len, const uint64_t* leaf_sibling_hashes,
+                                                const uint64_t* auth_paths, size_t path_len, const uint64_t* leaf_indexes,
+                                                uint8_t* ok, size_t n, void* stream);
 
 /* ---- Pedersen CRH / commitment over a twisted-Edwards curve -------------------------------- */
 /* pedersen::Parameters{generators: Vec<Vec<C>>} (R/crh/pedersen/mod.rs:28-31) and, when n_rand > 0,

@@ -16,6 +16,21 @@ static PoseidonDev to_dev(const host::PoseidonSchedule& S) {
 }
 
 template <class F, int T>
+static void run_sponge(const PoseidonDev& D, const u32* cs, const u32* in, long len, long n_out, long n, u32* out) {
+    u32 pm[8];
+    ld_elem(pm, cs + 8 * D.off_mod);
+    for (long i = 0; i < n; i++) pos_sponge<F, T>(out + 8 * n_out * i, n_out, in + 8 * len * i, len, D, cs, pm);
+}
+template <class F, int T>
+static void run_verify(const PoseidonDev& D, const u32* cs, const u32* root, const u32* leaves, long leaf_len, const u32* sib,
+                       const u32* paths, int plen, const unsigned long long* idx, unsigned char* ok, long n) {
+    u32 pm[8];
+    ld_elem(pm, cs + 8 * D.off_mod);
+    for (long i = 0; i < n; i++)
+        ok[i] = pos_verify_path<F, T>(leaves + 8 * leaf_len * i, leaf_len, sib + 8 * i, paths + 8 * (long)plen * i, plen, idx[i], root, D, cs, D, cs, pm);
+}
+
+template <class F, int T>
 static void run(const PoseidonDev& D, const u32* cs, const u32* in, long len, long n, u32* out) {
     u32 pm[8];
     ld_elem(pm, cs + 8 * D.off_mod);
@@ -72,5 +87,48 @@ extern "C" int host_poseidon_find_params(int field, int rate, int rf, int rp, in
     host::find_poseidon_ark_and_mds(F, (uint64_t)F.bits, rate, rf, rp, skip, a, m);
     memcpy(ark, a.data(), a.size() * 32);
     memcpy(mds, m.data(), m.size() * 32);
+    return 0;
+}
+
+static host::PoseidonSchedule make_schedule(int field, int rate, int cap, int rf, int rp, unsigned long long alpha,
+                                            const uint64_t* ark, const uint64_t* mds) {
+    host::Field F(host::field_modulus(field));
+    host::PoseidonParams P;
+    P.rate = rate; P.capacity = cap; P.full_rounds = rf; P.partial_rounds = rp; P.alpha = alpha;
+    int t = rate + cap;
+    P.ark.resize((size_t)(rf + rp) * t);
+    P.mds.resize((size_t)t * t);
+    memcpy(P.ark.data(), ark, P.ark.size() * 32);
+    memcpy(P.mds.data(), mds, P.mds.size() * 32);
+    return host::derive_schedule(F, P, true);
+}
+
+// absorb `len` then squeeze `n_out` native elements (t = 3 and 5, BLS12-381 Fr / BN254 Fr only: enough for the state machine)
+extern "C" int host_poseidon_sponge(int field, int rate, int cap, int rf, int rp, unsigned long long alpha, const uint64_t* ark,
+                                    const uint64_t* mds, const uint64_t* in, long len, long n_out, long n, uint64_t* out) {
+    host::PoseidonSchedule S = make_schedule(field, rate, cap, rf, rp, alpha, ark, mds);
+    PoseidonDev D = to_dev(S);
+    const u32* cs = reinterpret_cast<const u32*>(S.consts.data());
+    const u32* i32 = reinterpret_cast<const u32*>(in);
+    u32* o32 = reinterpret_cast<u32*>(out);
+    if (field == 0 && D.t == 3) run_sponge<Bls12_381_Fr, 3>(D, cs, i32, len, n_out, n, o32);
+    else if (field == 0 && D.t == 5) run_sponge<Bls12_381_Fr, 5>(D, cs, i32, len, n_out, n, o32);
+    else if (field == 1 && D.t == 3) run_sponge<Bn254_Fr, 3>(D, cs, i32, len, n_out, n, o32);
+    else return -1;
+    return 0;
+}
+
+extern "C" int host_poseidon_verify(int field, int rate, int cap, int rf, int rp, unsigned long long alpha, const uint64_t* ark,
+                                    const uint64_t* mds, const uint64_t* root, const uint64_t* leaves, long leaf_len,
+                                    const uint64_t* sib, const uint64_t* paths, int plen, const unsigned long long* idx,
+                                    unsigned char* ok, long n) {
+    host::PoseidonSchedule S = make_schedule(field, rate, cap, rf, rp, alpha, ark, mds);
+    PoseidonDev D = to_dev(S);
+    const u32* cs = reinterpret_cast<const u32*>(S.consts.data());
+    if (field == 0 && D.t == 3)
+        run_verify<Bls12_381_Fr, 3>(D, cs, (const u32*)root, (const u32*)leaves, leaf_len, (const u32*)sib, (const u32*)paths, plen, idx, ok, n);
+    else if (field == 2 && D.t == 3)
+        run_verify<Jubjub_Fr, 3>(D, cs, (const u32*)root, (const u32*)leaves, leaf_len, (const u32*)sib, (const u32*)paths, plen, idx, ok, n);
+    else return -1;
     return 0;
 }

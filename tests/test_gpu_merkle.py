@@ -111,3 +111,26 @@ def test_full_size_tree_properties():
     assert np.array_equal(nodes[n // 2 - 1 + bi], O.compress_batch(kids, threads=8))
     t2 = MerkleTree.new(cfg, cfg, leaves)
     assert np.array_equal(t2.non_leaf_nodes, nodes)
+
+
+def test_batched_path_verification():
+    """All 4096 paths of a tree verified in one launch; tampered leaf / sibling / index / root are rejected."""
+    _, ocfg = oracle_config("bls_default_r2")
+    cfg = product_config("bls_default_r2")
+    n = 4096
+    leaves = synth_elems(12, (n, 2), ocfg.p)
+    tree = MerkleTree.new(cfg, cfg, leaves)
+    proofs = [tree.generate_proof(i) for i in range(n)]
+    assert tree.verify_proofs_batch(proofs, leaves).all()
+    bad_leaves = leaves.copy()
+    bad_leaves[5, 0, 0] ^= np.uint64(1)
+    r = tree.verify_proofs_batch(proofs, bad_leaves)
+    assert not r[5] and r.sum() == n - 1
+    proofs[9].leaf_index ^= 2
+    proofs[11].auth_path[3] = proofs[12].auth_path[0]
+    r = tree.verify_proofs_batch(proofs, leaves)
+    assert not r[9] and not r[11] and r.sum() == n - 2
+    wrong_root = cfg.field.elements([123])[0]
+    assert not tree.verify_proofs_batch(proofs[:64], leaves[:64], wrong_root).any()
+    # agrees with the single-path mirror of Path::verify
+    assert proofs[100].verify(cfg, cfg, tree.root(), leaves[100])

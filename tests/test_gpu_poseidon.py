@@ -120,3 +120,41 @@ def test_large_batch_properties():
     assert np.array_equal(out[1000:3000], TwoToOneCRH.compress_batch(cfg, pairs[1000:3000]))
     idx = np.random.default_rng(0).choice(n, 512, replace=False)
     assert np.array_equal(out[idx], cref.Poseidon(ocfg).compress_batch(pairs[idx], threads=8))
+
+
+def test_sponge_surface_matches_oracle_state_machine():
+    """The reference's differential test shape (R/sponge/poseidon/tests.rs:68-239): random absorb/squeeze sequences;
+    here the GPU-backed mirror against the oracle's restatement of the same state machine, plus the KAT
+    (mod.rs:381-404) through squeeze_native_field_elements(3), squeeze_bytes/bits and the batched form."""
+    import random
+    from crypto_primitives_b200 import PoseidonSponge, absorb_squeeze_batch
+    f = cp.BLS12_381_FR
+    _, ocfg = oracle_config("bls_default_r2")
+    cfg = product_config("bls_default_r2")
+    s = PoseidonSponge.new(cfg)
+    s.absorb(f.elements([0, 1, 2]))
+    assert f.to_ints(s.squeeze_native_field_elements(3)) == [int(x) for x in kats()["sponge"]["squeeze3"]]
+    rnd = random.Random(5)
+    g, o = PoseidonSponge.new(cfg), OP.PoseidonSponge(ocfg)
+    for _ in range(25):
+        k = rnd.randrange(0, 5)
+        if rnd.random() < 0.5:
+            vals = [rnd.randrange(ocfg.p) for _ in range(k)]
+            g.absorb(f.elements(vals) if k else np.zeros((0, 4), dtype=np.uint64))
+            o.absorb(vals)
+        else:
+            assert f.to_ints(g.squeeze_native_field_elements(k)) == o.squeeze_native_field_elements(k)
+    # bytes / bits are truncations of native elements (mod.rs:259-291)
+    g2, o2 = PoseidonSponge.new(cfg), OP.PoseidonSponge(ocfg)
+    g2.absorb(f.elements([7, 8])); o2.absorb([7, 8])
+    e = o2.squeeze_native_field_elements(2)
+    assert g2.squeeze_bytes(40) == (e[0].to_bytes(32, "little")[:31] + e[1].to_bytes(32, "little")[:31])[:40]
+    # batched: n sponges, absorb L squeeze K
+    x = synth_elems(9, (300, 3), ocfg.p)
+    got = absorb_squeeze_batch(cfg, x, 5)
+    ints = cref.mont_to_ints(x, ocfg.p)
+    for i in (0, 17, 299):
+        o3 = OP.PoseidonSponge(ocfg)
+        o3.absorb(ints[3 * i:3 * i + 3])
+        assert f.to_ints(got[i]) == o3.squeeze_native_field_elements(5)
+    assert np.array_equal(absorb_squeeze_batch(cfg, x, 1)[:, 0], CRH.evaluate_batch(cfg, x))

@@ -91,3 +91,57 @@ def test_product_param_generation_matches_oracle(shim):
         ark, mds = OP.find_poseidon_ark_and_mds(p, bits, rate, rf, rp, 0)
         assert cref.mont_to_ints(a, p) == [x for r in ark for x in r]
         assert cref.mont_to_ints(m, p) == [x for r in mds for x in r]
+
+
+def _cfg_arrays(cfg):
+    p = cfg.p
+    return (cref.ints_to_mont([x for r in cfg.ark for x in r], p), cref.ints_to_mont([x for r in cfg.mds for x in r], p))
+
+
+@pytest.mark.parametrize("which,fid", [("bls_default_r2", 0), ("bn254_r2", 1)])
+def test_sponge_absorb_then_squeeze_many(shim, which, fid):
+    """absorb L, squeeze K native elements (R/sponge/poseidon/mod.rs:156-186,323-345) vs the oracle's state machine."""
+    _, cfg = oracle_config(which)
+    ark, mds = _cfg_arrays(cfg)
+    for L, K in ((0, 1), (0, 5), (1, 2), (2, 3), (3, 3), (5, 7), (4, 1)):
+        n = 5
+        inp = np.ascontiguousarray(synth_elems(300 + L, (n, max(L, 1)), cfg.p)[:, :L])
+        out = np.zeros((n, K, 4), dtype=np.uint64)
+        assert shim.host_poseidon_sponge(fid, cfg.rate, cfg.capacity, cfg.full_rounds, cfg.partial_rounds, C.c_ulonglong(cfg.alpha),
+                                         _P(ark), _P(mds), _P(inp), C.c_long(L), C.c_long(K), C.c_long(n), _P(out)) == 0
+        ints = cref.mont_to_ints(inp, cfg.p)
+        for i in range(n):
+            s = OP.PoseidonSponge(cfg)
+            s.absorb(ints[i * L:(i + 1) * L])
+            assert cref.mont_to_ints(out[i], cfg.p) == s.squeeze_native_field_elements(K), (L, K)
+
+
+def test_path_verification_device_code(shim):
+    """Path::verify (R/merkle_tree/mod.rs:172-212) as run by one GPU thread, on the reference's field-tree shape."""
+    from oracle import merkle as OM
+    _, cfg = oracle_config("jubjub_merkle_fixture")
+    ark, mds = _cfg_arrays(cfg)
+    n, L = 16, 3
+    lv = synth_elems(21, (n, L), cfg.p)
+    li = cref.mont_to_ints(lv, cfg.p)
+    h2 = lambda a, b: OP.two_to_one_compress(cfg, a, b)
+    T = OM.MerkleTree.new([li[L * i:L * i + L] for i in range(n)], lambda l: OP.crh_evaluate(cfg, l), h2, h2)
+    proofs = [T.generate_proof(i) for i in range(n)]
+    plen = len(proofs[0][1])
+    sib = cref.ints_to_mont([p[0] for p in proofs], cfg.p)
+    paths = cref.ints_to_mont([x for p in proofs for x in p[1]], cfg.p)
+    idx = np.arange(n, dtype=np.uint64)
+    root = cref.ints_to_mont([T.root()], cfg.p)
+    ok = np.zeros(n, dtype=np.uint8)
+
+    def run(root_arr, idx_arr):
+        assert shim.host_poseidon_verify(2, cfg.rate, cfg.capacity, cfg.full_rounds, cfg.partial_rounds, C.c_ulonglong(cfg.alpha), _P(ark),
+                                         _P(mds), _P(root_arr), _P(np.ascontiguousarray(lv)), C.c_long(L), _P(sib), _P(paths), plen,
+                                         idx_arr.ctypes.data_as(C.POINTER(C.c_ulonglong)), ok.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_long(n)) == 0
+        return ok.copy()
+
+    assert run(root, idx).all()
+    assert not run(cref.ints_to_mont([(T.root() + 1) % cfg.p], cfg.p), idx).any()          # wrong root (tests/mod.rs:236-262)
+    swapped = idx.copy(); swapped[[0, 1]] = swapped[[1, 0]]
+    r = run(root, swapped)
+    assert not r[0] and not r[1] and r[2:].all()                                            # wrong position
