@@ -136,11 +136,20 @@ cpb_status check_ctx(const cpb_poseidon_ctx* c) {
     return CPB_OK;
 }
 
+// Optional host mirrors (host-pointer entry points): when given, each subtree's stream also copies its slice of the
+// leaves in before hashing and its slices of leaf_nodes / of every level out afterwards, so PCIe transfers of one
+// subtree overlap the hashing of the others (copy engines + side streams); the top log2(S) levels follow at the end.
+struct MerkleHost {
+    const u32* leaves = nullptr;   // n * leaf_len elements
+    u32* leaf_nodes = nullptr;     // n elements
+    u32* nodes = nullptr;          // n - 1 elements
+};
+
 // Inner levels of subtree k of S (S a power of two) from the leaf digests, heap order: global level l has
 // 2^l nodes at [2^l - 1, 2^(l+1) - 1); subtree k owns the k-th 1/S of every level l >= log2 S
 // (new_with_leaf_digest, R/merkle_tree/mod.rs:424-523).  S = 1, k = 0 is the whole tree.
 cpb_status merkle_subtree_levels(cpb_poseidon_ctx* node, const u32* leaf_digests, size_t n, u32* nodes, size_t S, size_t k,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, const MerkleHost* H = nullptr) {
     int h = 0;
     while (((size_t)1 << h) < n) h++;
     int lg = 0;
@@ -150,6 +159,8 @@ cpb_status merkle_subtree_levels(cpb_poseidon_ctx* node, const u32* leaf_digests
         const u32* in = (l == h - 1) ? leaf_digests + 8 * (2 * k * cnt) : nodes + 8 * ((((size_t)1 << (l + 1)) - 1) + 2 * k * cnt);
         u32* out = nodes + 8 * ((((size_t)1 << l) - 1) + k * cnt);
         CPB_TRY(launch_crh(node, in, 2, out, cnt, st));
+        // copy the level out right behind its kernel: the transfer overlaps the next levels and the other subtrees
+        if (H) CPB_CUDA(cudaMemcpyAsync(H->nodes + (out - nodes), out, cnt * 32, cudaMemcpyDeviceToHost, st));
     }
     return CPB_OK;
 }
@@ -182,11 +193,17 @@ cpb_status ensure_side_streams(cpb_poseidon_ctx* c, size_t S) {
 
 // leaf hashing (when leaves != nullptr) + all inner levels, S subtrees on S side streams joined on `st`
 cpb_status merkle_build_streams(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, const u32* leaves, size_t leaf_len, size_t n,
-                                u32* leaf_nodes, u32* nodes, cudaStream_t st) {
+                                u32* leaf_nodes, u32* nodes, cudaStream_t st, const MerkleHost* H = nullptr) {
     size_t S = merkle_streams(n);
     if (S <= 1) {
+        if (H && H->leaves && n * leaf_len) CPB_CUDA(cudaMemcpyAsync((void*)leaves, H->leaves, n * leaf_len * 32, cudaMemcpyHostToDevice, st));
         if (leaves) CPB_TRY(launch_crh(leaf, leaves, leaf_len, leaf_nodes, n, st));
-        return merkle_levels(node, leaf_nodes, n, nodes, st);
+        CPB_TRY(merkle_levels(node, leaf_nodes, n, nodes, st));
+        if (H) {
+            CPB_CUDA(cudaMemcpyAsync(H->leaf_nodes, leaf_nodes, n * 32, cudaMemcpyDeviceToHost, st));
+            CPB_CUDA(cudaMemcpyAsync(H->nodes, nodes, (n - 1) * 32, cudaMemcpyDeviceToHost, st));
+        }
+        return CPB_OK;
     }
     CPB_TRY(ensure_side_streams(node, S));
     cudaEvent_t start = nullptr, done[8] = {};
@@ -198,8 +215,15 @@ cpb_status merkle_build_streams(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, 
         cudaStream_t sk = node->side[k];
         e = cudaStreamWaitEvent(sk, start, 0);
         if (e != cudaSuccess) break;
+        if (H && H->leaves && leaf_len)
+            e = cudaMemcpyAsync((void*)(leaves + 8 * leaf_len * (k * per)), H->leaves + 8 * leaf_len * (k * per), per * leaf_len * 32,
+                                cudaMemcpyHostToDevice, sk);
+        if (e != cudaSuccess) break;
         if (leaves) rc = launch_crh(leaf, leaves + 8 * leaf_len * (k * per), leaf_len, leaf_nodes + 8 * (k * per), per, sk);
-        if (rc == CPB_OK) rc = merkle_subtree_levels(node, leaf_nodes, n, nodes, S, k, sk);
+        if (rc == CPB_OK && H)
+            e = cudaMemcpyAsync(H->leaf_nodes + 8 * (k * per), leaf_nodes + 8 * (k * per), per * 32, cudaMemcpyDeviceToHost, sk);
+        if (e != cudaSuccess) break;
+        if (rc == CPB_OK) rc = merkle_subtree_levels(node, leaf_nodes, n, nodes, S, k, sk, H);
         if (rc != CPB_OK) break;
         e = cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventRecord(done[k], sk);
@@ -217,6 +241,7 @@ cpb_status merkle_build_streams(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, 
         size_t cnt = (size_t)1 << l;
         CPB_TRY(launch_crh(node, nodes + 8 * ((((size_t)1 << (l + 1)) - 1)), 2, nodes + 8 * (cnt - 1), cnt, st));
     }
+    if (H && S > 1) CPB_CUDA(cudaMemcpyAsync(H->nodes, nodes, (S - 1) * 32, cudaMemcpyDeviceToHost, st));
     return CPB_OK;
 }
 
@@ -542,11 +567,12 @@ cpb_status cpb_merkle_poseidon_build(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* n
     CPB_TRY(leaf->s_out.reserve(n * 32));
     CPB_TRY(leaf->s_aux.reserve((n - 1) * 32));
     cudaStream_t st = leaf->stream;
-    if (in_b) CPB_CUDA(cudaMemcpyAsync(leaf->s_in.ptr, leaves, in_b, cudaMemcpyHostToDevice, st));
-    CPB_TRY(cpb_merkle_poseidon_build_dev(leaf, node, (const uint64_t*)leaf->s_in.ptr, leaf_len, n,
-                                          (uint64_t*)leaf->s_out.ptr, (uint64_t*)leaf->s_aux.ptr, st));
-    CPB_CUDA(cudaMemcpyAsync(leaf_nodes, leaf->s_out.ptr, n * 32, cudaMemcpyDeviceToHost, st));
-    CPB_CUDA(cudaMemcpyAsync(non_leaf_nodes, leaf->s_aux.ptr, (n - 1) * 32, cudaMemcpyDeviceToHost, st));
+    if (leaf->device != node->device || leaf->field_id != node->field_id)
+        return fail(CPB_BAD_PARAMS, "leaf and node contexts must share device and field");
+    if (node->dev.rate < 2) return fail(CPB_UNSUPPORTED, "two-to-one with rate < 2 not supported");
+    MerkleHost H;
+    H.leaves = (const u32*)leaves; H.leaf_nodes = (u32*)leaf_nodes; H.nodes = (u32*)non_leaf_nodes;
+    CPB_TRY(merkle_build_streams(leaf, node, (const u32*)leaf->s_in.ptr, leaf_len, n, (u32*)leaf->s_out.ptr, (u32*)leaf->s_aux.ptr, st, &H));
     CPB_CUDA(cudaStreamSynchronize(st));
     return CPB_OK;
 }
