@@ -46,6 +46,7 @@ SIGNATURES = {
     "cpb_merkle_poseidon_from_digests": (C.c_int, [vp, u64p, C.c_size_t, u64p]),
     "cpb_merkle_poseidon_from_digests_dev": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
     "cpb_pedersen_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_int, u64p, C.c_size_t, u64p, C.c_int, C.POINTER(vp)]),
+    "cpb_pedersen_ctx_create_ex": (C.c_int, [C.c_int, C.c_int, C.c_int, u64p, C.c_size_t, u64p, C.c_int, C.c_int, C.POINTER(vp)]),
     "cpb_pedersen_ctx_destroy": (None, [vp]),
     "cpb_pedersen_crh_batch": (C.c_int, [vp, u8p, C.c_size_t, C.c_size_t, u64p, C.c_size_t]),
     "cpb_pedersen_crh_batch_dev": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp, C.c_size_t, vp]),

@@ -50,6 +50,7 @@ class Parameters:
     window: Window
     generators: np.ndarray
     randomness_generator: np.ndarray | None = None
+    chunk_bits: int = 0            # table lookup width on the device (0 = library default; 8..16); does not change results
     _ctx: dict = _f(default_factory=dict, repr=False)
 
     def __post_init__(self):
@@ -66,9 +67,9 @@ class Parameters:
         if h is None:
             out = N.vp()
             rg = self.randomness_generator
-            N.check(N.lib.cpb_pedersen_ctx_create(
+            N.check(N.lib.cpb_pedersen_ctx_create_ex(
                 self.curve.id, self.window.WINDOW_SIZE, self.window.NUM_WINDOWS, _u64(self.generators),
-                0 if rg is None else rg.shape[0], None if rg is None else _u64(rg), device, C.byref(out)))
+                0 if rg is None else rg.shape[0], None if rg is None else _u64(rg), device, self.chunk_bits, C.byref(out)))
             h = _Ctx(out.value)
             self._ctx[device] = h
         return h.handle

@@ -23,21 +23,26 @@ constexpr int kPedBlock = 256;
 constexpr int kEntryWords = 24;                    // 3 field elements
 constexpr int kChunkWords = 256 * kEntryWords;     // one 8-bit chunk: 24576 B
 constexpr unsigned kChunkBytes = kChunkWords * 4;
+#ifndef CPB_PEDERSEN_CHUNK_BITS
+#define CPB_PEDERSEN_CHUNK_BITS 8
+#endif
+constexpr int kDefaultChunkBits = CPB_PEDERSEN_CHUNK_BITS;
 
 struct PedersenDev {
-    int n_in_chunks;     // floor(WINDOW_SIZE*NUM_WINDOWS / 8): input bytes that can carry set bits
-    int n_rand_chunks;   // ceil(#randomness generators / 8), 0 without commitment parameters
+    int chunk_bits;      // 8: shared-memory (TMA-staged) tables; 9..16: L2 / HBM resident tables, gathered per lookup
+    int n_in_chunks;     // ceil(input bits that can be set / chunk_bits); with 8-bit chunks = input bytes
+    int n_rand_chunks;   // ceil(#randomness generators / chunk_bits), 0 without commitment parameters
     int zero;            // always 0 (see PoseidonDev::zero)
 };
 
 // consts layout (u32 words): [0..8) modulus limbs, [8..16) 2d (Montgomery), [16..24) d (Montgomery)
 template <class F>
 __global__ void __launch_bounds__(256)
-k_pedersen_table(const u32* __restrict__ consts, const u32* __restrict__ gens_xy, int n_gens, int n_chunks,
+k_pedersen_table(const u32* __restrict__ consts, const u32* __restrict__ gens_xy, int n_gens, int n_chunks, int chunk_bits,
                  u32* __restrict__ table, int zero) {
     long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (long)n_chunks * 256) return;
-    const int chunk = (int)(e >> 8), mask = (int)(e & 255);
+    if (e >= ((long)n_chunks << chunk_bits)) return;
+    const int chunk = (int)(e >> chunk_bits), mask = (int)(e & ((1 << chunk_bits) - 1));
     const u32* ct = consts + (int)threadIdx.x * zero;
     u32 pm[8], d2[8];
     ld_elem(pm, ct);
@@ -45,8 +50,8 @@ k_pedersen_table(const u32* __restrict__ consts, const u32* __restrict__ gens_xy
     TePoint acc;
     te_identity<F>(acc);
 #pragma unroll 1
-    for (int j = 0; j < 8; j++) {
-        int g = chunk * 8 + j;
+    for (int j = 0; j < chunk_bits; j++) {
+        int g = chunk * chunk_bits + j;
         if (!((mask >> j) & 1) || g >= n_gens) continue;
         u32 x[8], y[8], yp[8], ym[8], t2d[8];
         ld_elem(x, gens_xy + 16 * (long)g);
@@ -169,6 +174,55 @@ k_pedersen_hash(PedersenDev P, const u32* __restrict__ consts, const u32* __rest
     }
 }
 
+
+// Wide-chunk variant: `chunk_bits` (9..16) consecutive input bits select one of 2^chunk_bits subset sums per
+// lookup, so a hash needs bits/chunk_bits mixed additions instead of bits/8.  The tables no longer fit shared
+// memory (12 bits: 33 MB for a 1024-bit input, L2-resident on a B200; 16 bits: 400 MB in HBM); each thread gathers
+// its 96-byte entry with read-only 128-bit loads.  Trades the B200's large L2/HBM for integer-pipe work.
+template <class F>
+__global__ void __launch_bounds__(kPedBlock)
+k_pedersen_hash_gather(PedersenDev P, const u32* __restrict__ consts, const u32* __restrict__ table,
+                       const uint8_t* __restrict__ in, long len, long stride, const uint8_t* __restrict__ rand32,
+                       u32* __restrict__ out, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32* ct = consts + (int)threadIdx.x * P.zero;
+    u32 pm[8];
+    ld_elem(pm, ct);
+    const int cb = P.chunk_bits;
+    const u32 vmask = (1u << cb) - 1u;
+    const uint8_t* msg = in + i * stride;
+    const uint8_t* rnd = rand32 ? rand32 + i * 32 : nullptr;
+    const int total = P.n_in_chunks + (rand32 ? P.n_rand_chunks : 0);
+    TePoint acc;
+    te_identity<F>(acc);
+#pragma unroll 1
+    for (int c = 0; c < total; c++) {
+        const bool is_rand = c >= P.n_in_chunks;
+        const uint8_t* src = is_rand ? rnd : msg;
+        const long slen = is_rand ? 32 : len;
+        const long bit = (long)(is_rand ? c - P.n_in_chunks : c) * cb;
+        const long byte = bit >> 3;
+        u32 v = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (byte + k < slen) v |= (u32)__ldg(src + byte + k) << (8 * k);
+        v = (v >> (bit & 7)) & vmask;
+        const u32* e = table + (((long)c << cb) + v) * kEntryWords;
+        u32 yp[8], ym[8], t2d[8];
+        const uint4* e4 = reinterpret_cast<const uint4*>(e);
+        uint4 q0 = __ldg(e4), q1 = __ldg(e4 + 1), q2 = __ldg(e4 + 2), q3 = __ldg(e4 + 3), q4 = __ldg(e4 + 4), q5 = __ldg(e4 + 5);
+        yp[0] = q0.x; yp[1] = q0.y; yp[2] = q0.z; yp[3] = q0.w; yp[4] = q1.x; yp[5] = q1.y; yp[6] = q1.z; yp[7] = q1.w;
+        ym[0] = q2.x; ym[1] = q2.y; ym[2] = q2.z; ym[3] = q2.w; ym[4] = q3.x; ym[5] = q3.y; ym[6] = q3.z; ym[7] = q3.w;
+        t2d[0] = q4.x; t2d[1] = q4.y; t2d[2] = q4.z; t2d[3] = q4.w; t2d[4] = q5.x; t2d[5] = q5.y; t2d[6] = q5.z; t2d[7] = q5.w;
+        te_madd<F>(acc, yp, ym, t2d, pm);
+    }
+    u32* o = out + 32 * i;
+    st_elem(o, acc.X);
+    st_elem(o + 8, acc.Y);
+    st_elem(o + 16, acc.Z);
+}
+
 // Projective -> affine for n points with one field inversion per 32 points (Montgomery's trick along a
 // thread's own sequence of points: prefix products, one Fermat inversion, back-substitution).  A warp
 // pays for an inversion once whether its lanes invert the same or different values, so batching has to
@@ -246,6 +300,7 @@ struct cpb_pedersen_ctx {
     Scratch s_in, s_out, s_aux, s_rand;
 };
 
+extern "C" cpb_status cpb_pedersen_ctx_create_ex(int, int, int, const uint64_t*, size_t, const uint64_t*, int, int, cpb_pedersen_ctx**);
 extern "C" int cpb_poseidon_ctx_field(const cpb_poseidon_ctx* ctx);
 extern "C" int cpb_poseidon_ctx_device(const cpb_poseidon_ctx* ctx);
 
@@ -287,8 +342,12 @@ cpb_status launch_hash_f(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, siz
     CPB_TRY(ped_grid(k_pedersen_hash<F>, smem, c->sms, (long)n, grid));
     u32* proj = nullptr;
     CPB_CUDA(cudaMallocAsync((void**)&proj, n * 128, st));           // stream-ordered scratch: n x (X, Y, Z, prefix)
-    k_pedersen_hash<F><<<grid, kPedBlock, smem, st>>>(c->dev, c->d_consts, c->d_table, in, (long)len, (long)stride, rand32,
-                                                      proj, (long)n);
+    if (c->dev.chunk_bits == 8)
+        k_pedersen_hash<F><<<grid, kPedBlock, smem, st>>>(c->dev, c->d_consts, c->d_table, in, (long)len, (long)stride, rand32,
+                                                          proj, (long)n);
+    else
+        k_pedersen_hash_gather<F><<<(int)((n + kPedBlock - 1) / kPedBlock), kPedBlock, 0, st>>>(
+            c->dev, c->d_consts, c->d_table, in, (long)len, (long)stride, rand32, proj, (long)n);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) {
         long threads = ((long)n + 31) / 32;
@@ -369,7 +428,15 @@ extern "C" {
 
 cpb_status cpb_pedersen_ctx_create(int curve_id, int window_size, int num_windows, const uint64_t* generators_xy,
                                    size_t n_rand, const uint64_t* rand_generators_xy, int device, cpb_pedersen_ctx** out) {
+    return cpb_pedersen_ctx_create_ex(curve_id, window_size, num_windows, generators_xy, n_rand, rand_generators_xy, device, 0, out);
+}
+
+cpb_status cpb_pedersen_ctx_create_ex(int curve_id, int window_size, int num_windows, const uint64_t* generators_xy,
+                                      size_t n_rand, const uint64_t* rand_generators_xy, int device, int chunk_bits,
+                                      cpb_pedersen_ctx** out) {
     if (!out) return fail(CPB_NULL_POINTER, "null out");
+    if (chunk_bits == 0) chunk_bits = kDefaultChunkBits;
+    if (chunk_bits < 8 || chunk_bits > 16) return fail(CPB_BAD_PARAMS, "chunk_bits must be 8..16 (0 = default)");
     *out = nullptr;
     CurveInfo ci;
     if (!curve_info(curve_id, ci)) return fail(CPB_BAD_PARAMS, "unknown curve id %d", curve_id);
@@ -403,8 +470,11 @@ cpb_status cpb_pedersen_ctx_create(int curve_id, int window_size, int num_window
     cpb_pedersen_ctx* c = new cpb_pedersen_ctx();
     c->curve_id = curve_id; c->field_id = ci.field_id; c->device = device; c->sms = sm_count(device);
     c->window_size = window_size; c->num_windows = num_windows; c->n_rand = (int)n_rand; c->nbits = nbits;
-    c->dev.n_in_chunks = (int)(nbits / 8);
-    c->dev.n_rand_chunks = (int)((n_rand + 7) / 8);
+    c->dev.chunk_bits = chunk_bits;
+    const size_t settable = (nbits / 8) * 8;          // input bits that can ever be set (padding rule, crh/pedersen/mod.rs:94-99)
+    c->dev.n_in_chunks = (int)((settable + chunk_bits - 1) / chunk_bits);
+    c->dev.n_rand_chunks = (int)((n_rand + chunk_bits - 1) / chunk_bits);
+    const size_t chunk_words = ((size_t)kEntryWords) << chunk_bits;
     c->dev.zero = 0;
     const int total_chunks = c->dev.n_in_chunks + c->dev.n_rand_chunks;
     uint64_t consts[12];
@@ -414,7 +484,7 @@ cpb_status cpb_pedersen_ctx_create(int curve_id, int window_size, int num_window
     u32 *d_gens = nullptr, *d_rgens = nullptr;
     cudaError_t e = cudaMalloc(&c->d_consts, sizeof consts);
     if (e == cudaSuccess) e = cudaMemcpy(c->d_consts, consts, sizeof consts, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_table, (size_t)(total_chunks > 0 ? total_chunks : 1) * kChunkBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_table, (size_t)(total_chunks > 0 ? total_chunks : 1) * chunk_words * 4);
     if (e == cudaSuccess) e = cudaMalloc(&d_gens, nbits * 64);
     if (e == cudaSuccess) e = cudaMemcpy(d_gens, generators_xy, nbits * 64, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && n_rand) e = cudaMalloc(&d_rgens, n_rand * 64);
@@ -423,15 +493,15 @@ cpb_status cpb_pedersen_ctx_create(int curve_id, int window_size, int num_window
     if (e == cudaSuccess) {
         auto build = [&](const u32* gens, int n_gens, int n_chunks, u32* table) {
             if (n_chunks <= 0) return;
-            int grid = (n_chunks * 256 + 255) / 256;
-            // only the first floor(nbits/8)*8 input generators can ever be selected (see header)
+            long entries = (long)n_chunks << chunk_bits;
+            int grid = (int)((entries + 255) / 256);
             if (c->field_id == CPB_BLS12_381_FR)
-                k_pedersen_table<Bls12_381_Fr><<<grid, 256>>>(c->d_consts, gens, n_gens, n_chunks, table, 0);
+                k_pedersen_table<Bls12_381_Fr><<<grid, 256>>>(c->d_consts, gens, n_gens, n_chunks, chunk_bits, table, 0);
             else
-                k_pedersen_table<Bls12_377_Fr><<<grid, 256>>>(c->d_consts, gens, n_gens, n_chunks, table, 0);
+                k_pedersen_table<Bls12_377_Fr><<<grid, 256>>>(c->d_consts, gens, n_gens, n_chunks, chunk_bits, table, 0);
         };
-        build(d_gens, (int)nbits, c->dev.n_in_chunks, c->d_table);
-        build(d_rgens, (int)n_rand, c->dev.n_rand_chunks, c->d_table + (size_t)c->dev.n_in_chunks * kChunkWords);
+        build(d_gens, (int)settable, c->dev.n_in_chunks, c->d_table);
+        build(d_rgens, (int)n_rand, c->dev.n_rand_chunks, c->d_table + (size_t)c->dev.n_in_chunks * chunk_words);
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
     }

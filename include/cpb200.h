@@ -164,6 +164,12 @@ cpb_status cpb_merkle_poseidon_verify_batch_dev(cpb_poseidon_ctx* leaf_ctx, cpb_
 cpb_status cpb_pedersen_ctx_create(int curve_id, int window_size, int num_windows, const uint64_t* generators_xy,
                                    size_t n_rand, const uint64_t* rand_generators_xy, int device,
                                    cpb_pedersen_ctx** out);
+/* Same, choosing how many consecutive input bits one table lookup covers: 8 = 24 KB tables per chunk streamed through
+ * shared memory by TMA; 9..16 = larger L2/HBM-resident tables gathered per lookup (fewer additions per hash, results
+ * identical); 0 = library default. */
+cpb_status cpb_pedersen_ctx_create_ex(int curve_id, int window_size, int num_windows, const uint64_t* generators_xy,
+                                      size_t n_rand, const uint64_t* rand_generators_xy, int device, int chunk_bits,
+                                      cpb_pedersen_ctx** out);
 void cpb_pedersen_ctx_destroy(cpb_pedersen_ctx* ctx);
 
 /* n x pedersen::CRH::evaluate (R/crh/pedersen/mod.rs:76-129): input i is the `len` bytes at

@@ -52,6 +52,25 @@ def test_crh_matches_oracle(ws, nw, lens):
     assert tuple(cp.BLS12_381_FR.to_ints(CRH.evaluate(prm, one))) == OPD.crh_evaluate(oprm, ow, one)
 
 
+@pytest.mark.parametrize("chunk_bits", [9, 12, 16])
+@pytest.mark.parametrize("ws,nw,ln", [(4, 256, 128), (4, 256, 33), (127, 9, 142), (4, 9, 4)])
+def test_wide_table_chunks_give_identical_results(chunk_bits, ws, nw, ln):
+    """cpb_pedersen_ctx_create_ex: 9..16 input bits per table lookup (L2/HBM-resident tables, gathered) instead of 8
+    (shared-memory tables): CRH, x-only and commitment outputs must not change."""
+    ow, oprm, oc, prm8 = setup(ws, nw, 9, commitment=True)
+    prm = Parameters(prm8.curve, prm8.window, prm8.generators, prm8.randomness_generator, chunk_bits=chunk_bits)
+    n = 200
+    inp = np.ascontiguousarray(cref.synth_bytes(900 + ln, n * ln).reshape(n, ln))
+    inp[0, :] = 0xFF
+    exp = oc.batch(inp, threads=8)
+    assert np.array_equal(CRH.evaluate_batch(prm, inp), exp)
+    assert np.array_equal(PedersenCRHCompressor.evaluate_batch(prm, inp), exp[:, 0])
+    rs = [OF.SplitMix64(700 + i).field(OF.JUBJUB_FR) for i in range(n)]
+    rs[0] = OF.JUBJUB_FR - 1
+    rb = randomness_bytes(cp.curves.JUBJUB, rs)
+    assert np.array_equal(Commitment.commit_batch(prm, inp, rb), oc.batch(inp, rb, threads=8))
+
+
 def test_input_too_long_is_rejected():
     """R/crh/pedersen/mod.rs:82-89 panics; the ABI returns CPB_BAD_LENGTH."""
     _, _, _, prm = setup(4, 9, 5)
