@@ -435,7 +435,16 @@ cpb_status cpb_pedersen_ctx_create_ex(int curve_id, int window_size, int num_win
                                       size_t n_rand, const uint64_t* rand_generators_xy, int device, int chunk_bits,
                                       cpb_pedersen_ctx** out) {
     if (!out) return fail(CPB_NULL_POINTER, "null out");
-    if (chunk_bits == 0) chunk_bits = kDefaultChunkBits;
+    if (chunk_bits == 0) {
+        // default: the widest lookup whose tables stay under 1 GiB (16 bits: 0.5 GB for a 1024-bit input + 252
+        // randomness generators; measured 1.9x the 8-bit shared-memory path), else 12 (L2-resident), else 8
+        const size_t bits_total = (size_t)window_size * num_windows + n_rand;
+        chunk_bits = kDefaultChunkBits;
+        for (int cand : {16, 12}) {
+            size_t chunks = (bits_total + cand - 1) / cand + 1;
+            if (chunks * (((size_t)kEntryWords * 4) << cand) <= ((size_t)1 << 30)) { chunk_bits = cand; break; }
+        }
+    }
     if (chunk_bits < 8 || chunk_bits > 16) return fail(CPB_BAD_PARAMS, "chunk_bits must be 8..16 (0 = default)");
     *out = nullptr;
     CurveInfo ci;
