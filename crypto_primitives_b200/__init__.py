@@ -12,9 +12,10 @@ from .sponge.poseidon import (PoseidonConfig, PoseidonSponge, absorb_squeeze_bat
                               get_default_poseidon_parameters)
 from .crh import poseidon as crh_poseidon
 from .crh import pedersen as crh_pedersen
+from .crh import bowe_hopwood as crh_bowe_hopwood
 from .commitment import pedersen as commitment_pedersen
 from . import curves
 from . import merkle_tree
 
 __all__ = ["Field", "FIELDS", "BLS12_381_FR", "BN254_FR", "JUBJUB_FR", "BLS12_377_FR", "PoseidonConfig", "PoseidonSponge", "absorb_squeeze_batch",
-           "find_poseidon_ark_and_mds", "get_default_poseidon_parameters", "crh_poseidon", "crh_pedersen", "commitment_pedersen", "curves", "merkle_tree"]
+           "find_poseidon_ark_and_mds", "get_default_poseidon_parameters", "crh_poseidon", "crh_pedersen", "crh_bowe_hopwood", "commitment_pedersen", "curves", "merkle_tree"]

@@ -56,6 +56,13 @@ SIGNATURES = {
     "cpb_pedersen_two_to_one_batch_dev": (C.c_int, [vp, vp, vp, C.c_size_t, vp, vp]),
     "cpb_pedersen_commit_batch": (C.c_int, [vp, u8p, C.c_size_t, C.c_size_t, u8p, u64p, C.c_size_t]),
     "cpb_pedersen_commit_batch_dev": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp, vp, C.c_size_t, vp]),
+    "cpb_bowe_hopwood_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_int, u64p, C.c_int, C.POINTER(vp)]),
+    "cpb_bowe_hopwood_ctx_destroy": (None, [vp]),
+    "cpb_bowe_hopwood_crh_batch": (C.c_int, [vp, u8p, C.c_size_t, C.c_size_t, u64p, C.c_size_t]),
+    "cpb_bowe_hopwood_crh_batch_dev": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp, C.c_size_t, vp]),
+    "cpb_bowe_hopwood_two_to_one_batch": (C.c_int, [vp, u64p, u64p, C.c_size_t]),
+    "cpb_bowe_hopwood_two_to_one_batch_dev": (C.c_int, [vp, vp, vp, C.c_size_t, vp, vp]),
+    "cpb_bowe_hopwood_two_to_one_scratch_bytes": (C.c_size_t, [vp, C.c_size_t]),
     "cpb_merkle_pedersen_build": (C.c_int, [vp, vp, u8p, C.c_size_t, C.c_size_t, u64p, u64p]),
     "cpb_merkle_pedersen_build_dev": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, vp, vp]),
     "cpb_merkle_mixed_build": (C.c_int, [vp, vp, u8p, C.c_size_t, C.c_size_t, u64p, u64p]),

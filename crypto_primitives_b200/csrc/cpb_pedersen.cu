@@ -284,6 +284,155 @@ __global__ void k_points_to_bytes(const u32* __restrict__ children, u32* __restr
     st_elem(bytes_out + 8 * i, a);
 }
 
+
+// ======================================================================= Bowe-Hopwood Pedersen CRH
+// bowe_hopwood::CRH::evaluate (R/crh/bowe_hopwood/mod.rs:115-185): 3-bit chunk k of the input selects
+// (1 + c0 + 2*c1) * (-1)^c2 * generators[k / WS][k % WS]; only the chunks the input covers contribute
+// (an all-zero chunk still adds its generator once).  Same table idea as above: m consecutive chunks
+// (3m bits) select one of 2^(3m) precomputed sums; the chunks left over at the end of an input use
+// per-chunk 8-entry tables.
+
+// table3[k][v], v = c0 + 2*c1 + 4*c2: affine-Niels of the encoded multiple of generator k
+template <class F>
+__global__ void __launch_bounds__(128)
+k_bh_table3(const u32* __restrict__ consts, const u32* __restrict__ gens_xy, int n_gens, u32* __restrict__ table3, int zero) {
+    long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long)n_gens * 8) return;
+    const int k = (int)(e >> 3), v = (int)(e & 7);
+    const u32* ct = consts + (int)threadIdx.x * zero;
+    u32 pm[8], d2[8], x[8], y[8], yp[8], ym[8], t2d[8];
+    ld_elem(pm, ct);
+    ld_elem(d2, ct + 8);
+    ld_elem(x, gens_xy + 16 * (long)k);
+    ld_elem(y, gens_xy + 16 * (long)k + 8);
+    te_niels<F>(yp, ym, t2d, x, y, d2, pm);
+    TePoint acc;
+    te_identity<F>(acc);
+    const int mult = 1 + (v & 1) + 2 * ((v >> 1) & 1);
+#pragma unroll 1
+    for (int r = 0; r < mult; r++) te_madd<F>(acc, yp, ym, t2d, pm);
+    u32 zi[8];
+    fp_inv<F>(zi, acc.Z, pm);
+    fp_mul<F>(x, acc.X, zi, pm);
+    fp_mul<F>(y, acc.Y, zi, pm);
+    if (v & 4) {                                   // -(x, y) = (-x, y)
+        u32 z0[8];
+        fp_zero(z0);
+        fp_sub<F>(x, z0, x);
+    }
+    te_niels<F>(yp, ym, t2d, x, y, d2, pm);
+    u32* o = table3 + e * kEntryWords;
+    st_elem(o, yp);
+    st_elem(o + 8, ym);
+    st_elem(o + 16, t2d);
+}
+
+// table[g][value]: sum over the m chunks of group g of table3[g*m + j][(value >> 3j) & 7]
+template <class F>
+__global__ void __launch_bounds__(128)
+k_bh_table_group(const u32* __restrict__ consts, const u32* __restrict__ table3, int n_gens, int n_groups, int m,
+                 u32* __restrict__ table, int zero) {
+    long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int gb = 3 * m;
+    if (e >= ((long)n_groups << gb)) return;
+    const int g = (int)(e >> gb);
+    const u32 value = (u32)(e & ((1L << gb) - 1));
+    const u32* ct = consts + (int)threadIdx.x * zero;
+    u32 pm[8], d2[8];
+    ld_elem(pm, ct);
+    ld_elem(d2, ct + 8);
+    TePoint acc;
+    te_identity<F>(acc);
+#pragma unroll 1
+    for (int j = 0; j < m; j++) {
+        int k = g * m + j;
+        if (k >= n_gens) break;
+        const u32* t = table3 + ((long)k * 8 + ((value >> (3 * j)) & 7u)) * kEntryWords;
+        u32 yp[8], ym[8], t2d[8];
+        ld_elem(yp, t);
+        ld_elem(ym, t + 8);
+        ld_elem(t2d, t + 16);
+        te_madd<F>(acc, yp, ym, t2d, pm);
+    }
+    u32 zi[8], x[8], y[8], yp[8], ym[8], t2d[8];
+    fp_inv<F>(zi, acc.Z, pm);
+    fp_mul<F>(x, acc.X, zi, pm);
+    fp_mul<F>(y, acc.Y, zi, pm);
+    te_niels<F>(yp, ym, t2d, x, y, d2, pm);
+    u32* o = table + e * kEntryWords;
+    st_elem(o, yp);
+    st_elem(o + 8, ym);
+    st_elem(o + 16, t2d);
+}
+
+__device__ __forceinline__ u32 bits_at(const uint8_t* src, long slen, long bit, int nbits) {
+    const long byte = bit >> 3;
+    u32 v = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if (byte + k < slen) v |= (u32)__ldg(src + byte + k) << (8 * k);
+    return (v >> (bit & 7)) & ((1u << nbits) - 1u);
+}
+
+__device__ __forceinline__ void gather_entry(u32* yp, u32* ym, u32* t2d, const u32* e) {
+    const uint4* e4 = reinterpret_cast<const uint4*>(e);
+    uint4 q0 = __ldg(e4), q1 = __ldg(e4 + 1), q2 = __ldg(e4 + 2), q3 = __ldg(e4 + 3), q4 = __ldg(e4 + 4), q5 = __ldg(e4 + 5);
+    yp[0] = q0.x; yp[1] = q0.y; yp[2] = q0.z; yp[3] = q0.w; yp[4] = q1.x; yp[5] = q1.y; yp[6] = q1.z; yp[7] = q1.w;
+    ym[0] = q2.x; ym[1] = q2.y; ym[2] = q2.z; ym[3] = q2.w; ym[4] = q3.x; ym[5] = q3.y; ym[6] = q3.z; ym[7] = q3.w;
+    t2d[0] = q4.x; t2d[1] = q4.y; t2d[2] = q4.z; t2d[3] = q4.w; t2d[4] = q5.x; t2d[5] = q5.y; t2d[6] = q5.z; t2d[7] = q5.w;
+}
+
+// one hash per thread; out = n x (X, Y, Z, -) projective (normalised by k_pedersen_normalise, mode 1 = x only)
+template <class F>
+__global__ void __launch_bounds__(kPedBlock)
+k_bh_hash(const u32* __restrict__ consts, const u32* __restrict__ table, const u32* __restrict__ table3, int m, int n_full,
+          int n_tail, const uint8_t* __restrict__ in, long len, long stride, u32* __restrict__ out, long n, int zero) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 pm[8];
+    ld_elem(pm, consts + (int)threadIdx.x * zero);
+    const uint8_t* msg = in + i * stride;
+    const int gb = 3 * m;
+    TePoint acc;
+    te_identity<F>(acc);
+    u32 yp[8], ym[8], t2d[8];
+#pragma unroll 1
+    for (int g = 0; g < n_full; g++) {
+        u32 v = bits_at(msg, len, (long)g * gb, gb);
+        gather_entry(yp, ym, t2d, table + (((long)g << gb) + v) * kEntryWords);
+        te_madd<F>(acc, yp, ym, t2d, pm);
+    }
+#pragma unroll 1
+    for (int j = 0; j < n_tail; j++) {
+        const long k = (long)n_full * m + j;
+        u32 v = bits_at(msg, len, 3 * k, 3);
+        gather_entry(yp, ym, t2d, table3 + (k * 8 + v) * kEntryWords);
+        te_madd<F>(acc, yp, ym, t2d, pm);
+    }
+    u32* o = out + 32 * i;
+    st_elem(o, acc.X);
+    st_elem(o + 8, acc.Y);
+    st_elem(o + 16, acc.Z);
+}
+
+// n x (left, right) base-field elements -> n x stride bytes: canonical LE left || right (64 bytes), rest untouched (zeroed by the caller)
+template <class F>
+__global__ void k_bh_children_to_bytes(const u32* __restrict__ children, uint8_t* __restrict__ out, long n, long stride, long keep) {
+    long e = (long)blockIdx.x * blockDim.x + threadIdx.x;     // element index: 2 per node
+    if (e >= 2 * n) return;
+    u32 a[8], one[8], pm[8];
+    ld_elem(a, children + 8 * e);
+    fp_zero(one);
+    one[0] = 1;
+    fp_modulus<F>(pm);
+    fp_mul<F>(a, a, one, pm);
+    uint8_t* o = out + (e >> 1) * stride + (e & 1) * 32;
+    const long base = (e & 1) * 32;
+#pragma unroll 1
+    for (int b = 0; b < 32; b++)
+        if (base + b < keep) o[b] = (uint8_t)(a[b >> 2] >> (8 * (b & 3)));
+}
+
 }  // namespace cpb
 
 using namespace cpb;
@@ -692,6 +841,203 @@ cpb_status cpb_merkle_mixed_build(cpb_pedersen_ctx* leaf, cpb_poseidon_ctx* node
     CPB_CUDA(cudaMemcpyAsync(leaf_nodes, d_leaf, n * 32, cudaMemcpyDeviceToHost, st));
     CPB_CUDA(cudaMemcpyAsync(non_leaf_nodes, d_nodes, (n - 1) * 32, cudaMemcpyDeviceToHost, st));
     CPB_CUDA(cudaStreamSynchronize(st));
+    return CPB_OK;
+}
+
+}  // extern "C"
+
+// ======================================================================= Bowe-Hopwood C ABI
+struct cpb_bowe_hopwood_ctx {
+    int curve_id = 0, field_id = 0, device = 0, sms = 148;
+    int window_size = 0, num_windows = 0, m = 4;
+    size_t n_gens = 0;
+    u32* d_consts = nullptr;
+    u32* d_table3 = nullptr;
+    u32* d_table = nullptr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    Scratch s_in, s_out, s_aux;
+};
+
+namespace {
+
+template <class F>
+cpb_status bh_launch_f(cpb_bowe_hopwood_ctx* c, const uint8_t* in, size_t len, size_t stride, u32* out_x, size_t n, cudaStream_t st) {
+    const size_t nc3 = (8 * len + 2) / 3;                         // chunks the (zero-padded) input covers, mod.rs:133-140
+    const int n_full = (int)(nc3 / c->m), n_tail = (int)(nc3 % c->m);
+    u32* proj = nullptr;
+    CPB_CUDA(cudaMallocAsync((void**)&proj, n * 128, st));
+    k_bh_hash<F><<<(int)((n + kPedBlock - 1) / kPedBlock), kPedBlock, 0, st>>>(c->d_consts, c->d_table, c->d_table3, c->m, n_full, n_tail,
+                                                                               in, (long)len, (long)stride, proj, (long)n, 0);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        long threads = ((long)n + 31) / 32;
+        k_pedersen_normalise<F><<<(int)((threads + 127) / 128), 128, 0, st>>>(c->d_consts, proj, out_x, (long)n, 1, 0);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(proj, st);
+    if (e != cudaSuccess) return fail(CPB_CUDA_ERROR, "bowe-hopwood launch failed: %s", cudaGetErrorString(e));
+    return CPB_OK;
+}
+cpb_status bh_launch(cpb_bowe_hopwood_ctx* c, const uint8_t* in, size_t len, size_t stride, u32* out_x, size_t n, cudaStream_t st) {
+    if (n == 0) return CPB_OK;
+    if (len * 8 > c->n_gens * 3)   // R/crh/bowe_hopwood/mod.rs:121-129 (panic)
+        return fail(CPB_BAD_LENGTH, "incorrect input bitlength %zu for window params %dx%dx3", len * 8, c->window_size, c->num_windows);
+    switch (c->field_id) {
+        case CPB_BLS12_381_FR: return bh_launch_f<Bls12_381_Fr>(c, in, len, stride, out_x, n, st);
+        case CPB_BLS12_377_FR: return bh_launch_f<Bls12_377_Fr>(c, in, len, stride, out_x, n, st);
+    }
+    return fail(CPB_UNSUPPORTED, "no kernel for base field %d", c->field_id);
+}
+// TwoToOneCRH::evaluate buffer: INPUT_SIZE_BITS / 8 bytes with INPUT_SIZE_BITS = WINDOW_SIZE * NUM_WINDOWS (mod.rs:69, 218)
+size_t bh_two_to_one_len(const cpb_bowe_hopwood_ctx* c) { return c->n_gens / 8; }
+size_t bh_two_to_one_stride(const cpb_bowe_hopwood_ctx* c) {
+    size_t l = bh_two_to_one_len(c);
+    if (l < 64) l = 64;
+    return (l + 15) & ~(size_t)15;
+}
+cpb_status bh_two_to_one_dev(cpb_bowe_hopwood_ctx* c, const u32* children, u32* out_x, size_t n, uint8_t* scratch, cudaStream_t st) {
+    if (n == 0) return CPB_OK;
+    const size_t len = bh_two_to_one_len(c), stride = bh_two_to_one_stride(c);
+    CPB_CUDA(cudaMemsetAsync(scratch, 0, n * stride, st));
+    int grid = (int)((2 * n + 255) / 256);
+    if (c->field_id == CPB_BLS12_381_FR) k_bh_children_to_bytes<Bls12_381_Fr><<<grid, 256, 0, st>>>(children, scratch, (long)n, (long)stride, (long)len);
+    else k_bh_children_to_bytes<Bls12_377_Fr><<<grid, 256, 0, st>>>(children, scratch, (long)n, (long)stride, (long)len);
+    CPB_CUDA(cudaGetLastError());
+    return bh_launch(c, scratch, len, stride, out_x, n, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+cpb_status cpb_bowe_hopwood_ctx_create(int curve_id, int window_size, int num_windows, const uint64_t* generators_xy, int device,
+                                       cpb_bowe_hopwood_ctx** out) {
+    if (!out) return fail(CPB_NULL_POINTER, "null out");
+    *out = nullptr;
+    CurveInfo ci;
+    if (!curve_info(curve_id, ci)) return fail(CPB_BAD_PARAMS, "unknown curve id %d", curve_id);
+    if (window_size < 1 || num_windows < 1 || (size_t)window_size * num_windows > (1u << 16))
+        return fail(CPB_BAD_PARAMS, "bad window %dx%d", window_size, num_windows);
+    if (!generators_xy) return fail(CPB_NULL_POINTER, "null generators");
+    host::Field F(host::field_modulus(ci.field_id));
+    host::Fe d = ci.d_is_ratio ? F.neg(F.mul(F.from_u64(ci.num), F.inv(F.from_u64(ci.den)))) : F.from_u64(ci.num);
+    host::Fe d2 = F.add(d, d);
+    const size_t n_gens = (size_t)window_size * num_windows;
+    for (size_t i = 0; i < n_gens; i++) {
+        host::Fe x, y;
+        memcpy(x.l, generators_xy + 8 * i, 32);
+        memcpy(y.l, generators_xy + 8 * i + 4, 32);
+        host::Fe xx = F.mul(x, x), yy = F.mul(y, y);
+        if (!F.is_canonical(x) || !F.is_canonical(y) || !(F.sub(yy, xx) == F.add(F.one(), F.mul(d, F.mul(xx, yy)))))
+            return fail(CPB_BAD_PARAMS, "generator %zu is not a reduced point on the curve", i);
+    }
+    DeviceGuard g(device);
+    if (!g.ok) { cudaGetLastError(); return fail(CPB_NO_DEVICE, "cudaSetDevice(%d) failed: no usable CUDA device", device); }
+    int major = 0;
+    CPB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return fail(CPB_NO_DEVICE, "device %d is sm_%d0; this library is built for sm_100a only", device, major);
+
+    cpb_bowe_hopwood_ctx* c = new cpb_bowe_hopwood_ctx();
+    c->curve_id = curve_id; c->field_id = ci.field_id; c->device = device; c->sms = sm_count(device);
+    c->window_size = window_size; c->num_windows = num_windows; c->n_gens = n_gens;
+    c->m = 5;                                                    // 15-bit lookups unless the tables would exceed 1 GiB
+    if (((n_gens + 4) / 5) * (((size_t)kEntryWords * 4) << 15) > ((size_t)1 << 30)) c->m = 4;
+    const size_t n_groups = (n_gens + c->m - 1) / c->m;
+    uint64_t consts[12];
+    memcpy(consts, F.p, 32);
+    memcpy(consts + 4, d2.l, 32);
+    memcpy(consts + 8, d.l, 32);
+    u32* d_gens = nullptr;
+    cudaError_t e = cudaMalloc(&c->d_consts, sizeof consts);
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_consts, consts, sizeof consts, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_table3, n_gens * 8 * kEntryWords * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_table, (n_groups << (3 * c->m)) * kEntryWords * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_gens, n_gens * 64);
+    if (e == cudaSuccess) e = cudaMemcpy(d_gens, generators_xy, n_gens * 64, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        const long e3 = (long)n_gens * 8, eg = (long)n_groups << (3 * c->m);
+        if (c->field_id == CPB_BLS12_381_FR) {
+            k_bh_table3<Bls12_381_Fr><<<(int)((e3 + 127) / 128), 128>>>(c->d_consts, d_gens, (int)n_gens, c->d_table3, 0);
+            k_bh_table_group<Bls12_381_Fr><<<(int)((eg + 127) / 128), 128>>>(c->d_consts, c->d_table3, (int)n_gens, (int)n_groups, c->m, c->d_table, 0);
+        } else {
+            k_bh_table3<Bls12_377_Fr><<<(int)((e3 + 127) / 128), 128>>>(c->d_consts, d_gens, (int)n_gens, c->d_table3, 0);
+            k_bh_table_group<Bls12_377_Fr><<<(int)((eg + 127) / 128), 128>>>(c->d_consts, c->d_table3, (int)n_gens, (int)n_groups, c->m, c->d_table, 0);
+        }
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    if (d_gens) cudaFree(d_gens);
+    if (e != cudaSuccess) {
+        if (c->d_consts) cudaFree(c->d_consts);
+        if (c->d_table3) cudaFree(c->d_table3);
+        if (c->d_table) cudaFree(c->d_table);
+        if (c->stream) cudaStreamDestroy(c->stream);
+        delete c;
+        return fail(CPB_CUDA_ERROR, "bowe-hopwood context build failed: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return CPB_OK;
+}
+
+void cpb_bowe_hopwood_ctx_destroy(cpb_bowe_hopwood_ctx* c) {
+    if (!c) return;
+    DeviceGuard g(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->d_consts) cudaFree(c->d_consts);
+    if (c->d_table3) cudaFree(c->d_table3);
+    if (c->d_table) cudaFree(c->d_table);
+    c->s_in.release(); c->s_out.release(); c->s_aux.release();
+    delete c;
+}
+
+cpb_status cpb_bowe_hopwood_crh_batch_dev(cpb_bowe_hopwood_ctx* c, const uint8_t* in, size_t len, size_t stride, uint64_t* out_x,
+                                          size_t n, void* stream) {
+    if (!c) return fail(CPB_NULL_POINTER, "null context");
+    DeviceGuard g(c->device);
+    return bh_launch(c, in, len, stride, (u32*)out_x, n, (cudaStream_t)stream);
+}
+cpb_status cpb_bowe_hopwood_two_to_one_batch_dev(cpb_bowe_hopwood_ctx* c, const uint64_t* children_x, uint64_t* out_x, size_t n,
+                                                 void* scratch, void* stream) {
+    if (!c) return fail(CPB_NULL_POINTER, "null context");
+    if (n && !scratch) return fail(CPB_NULL_POINTER, "null scratch");
+    DeviceGuard g(c->device);
+    return bh_two_to_one_dev(c, (const u32*)children_x, (u32*)out_x, n, (uint8_t*)scratch, (cudaStream_t)stream);
+}
+size_t cpb_bowe_hopwood_two_to_one_scratch_bytes(const cpb_bowe_hopwood_ctx* c, size_t n) { return c ? n * bh_two_to_one_stride(c) : 0; }
+
+cpb_status cpb_bowe_hopwood_crh_batch(cpb_bowe_hopwood_ctx* c, const uint8_t* in, size_t len, size_t stride, uint64_t* out_x, size_t n) {
+    if (!c) return fail(CPB_NULL_POINTER, "null context");
+    if (len * 8 > c->n_gens * 3)
+        return fail(CPB_BAD_LENGTH, "incorrect input bitlength %zu for window params %dx%dx3", len * 8, c->window_size, c->num_windows);
+    if (n == 0) return CPB_OK;
+    if ((!in && len) || !out_x) return fail(CPB_NULL_POINTER, "null buffer");
+    if (stride < len) return fail(CPB_BAD_PARAMS, "stride < len");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    size_t in_b = (n - 1) * stride + len;
+    CPB_TRY(c->s_in.reserve(in_b ? in_b : 16));
+    CPB_TRY(c->s_out.reserve(n * 32));
+    if (in_b) CPB_CUDA(cudaMemcpyAsync(c->s_in.ptr, in, in_b, cudaMemcpyHostToDevice, c->stream));
+    CPB_TRY(bh_launch(c, (const uint8_t*)c->s_in.ptr, len, stride, (u32*)c->s_out.ptr, n, c->stream));
+    CPB_CUDA(cudaMemcpyAsync(out_x, c->s_out.ptr, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    return CPB_OK;
+}
+cpb_status cpb_bowe_hopwood_two_to_one_batch(cpb_bowe_hopwood_ctx* c, const uint64_t* children_x, uint64_t* out_x, size_t n) {
+    if (!c) return fail(CPB_NULL_POINTER, "null context");
+    if (n == 0) return CPB_OK;
+    if (!children_x || !out_x) return fail(CPB_NULL_POINTER, "null buffer");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    CPB_TRY(c->s_in.reserve(n * 64));
+    CPB_TRY(c->s_aux.reserve(n * bh_two_to_one_stride(c)));
+    CPB_TRY(c->s_out.reserve(n * 32));
+    CPB_CUDA(cudaMemcpyAsync(c->s_in.ptr, children_x, n * 64, cudaMemcpyHostToDevice, c->stream));
+    CPB_TRY(bh_two_to_one_dev(c, (const u32*)c->s_in.ptr, (u32*)c->s_out.ptr, n, (uint8_t*)c->s_aux.ptr, c->stream));
+    CPB_CUDA(cudaMemcpyAsync(out_x, c->s_out.ptr, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    CPB_CUDA(cudaStreamSynchronize(c->stream));
     return CPB_OK;
 }
 

@@ -63,6 +63,7 @@ typedef enum cpb_curve {
 
 typedef struct cpb_poseidon_ctx cpb_poseidon_ctx;
 typedef struct cpb_pedersen_ctx cpb_pedersen_ctx;
+typedef struct cpb_bowe_hopwood_ctx cpb_bowe_hopwood_ctx;
 
 const char* cpb_last_error(void);
 int cpb_version(void);
@@ -200,6 +201,26 @@ cpb_status cpb_pedersen_commit_batch(cpb_pedersen_ctx* ctx, const uint8_t* in, s
                                      const uint8_t* randomness_le32, uint64_t* out_xy, size_t n);
 cpb_status cpb_pedersen_commit_batch_dev(cpb_pedersen_ctx* ctx, const uint8_t* in, size_t len, size_t stride,
                                          const uint8_t* randomness_le32, uint64_t* out_xy, size_t n, void* stream);
+
+/* ---- Bowe-Hopwood Pedersen CRH (R/crh/bowe_hopwood/mod.rs) ------------------------------------------ */
+/* bowe_hopwood::Parameters{generators: Vec<Vec<TEProjective<P>>>} (mod.rs:33-37): num_windows segments of
+ * window_size generators (one per 3-bit chunk), affine (x, y), generators[w][j] at index w*window_size + j. */
+cpb_status cpb_bowe_hopwood_ctx_create(int curve_id, int window_size, int num_windows, const uint64_t* generators_xy, int device,
+                                       cpb_bowe_hopwood_ctx** out);
+void cpb_bowe_hopwood_ctx_destroy(cpb_bowe_hopwood_ctx* ctx);
+/* n x bowe_hopwood::CRH::evaluate (mod.rs:115-185): output = x-coordinate (one base-field element).  Only the
+ * 3-bit chunks the input covers contribute, so the digest depends on `len`.  len*8 > 3*window_size*num_windows
+ * -> CPB_BAD_LENGTH (the reference panics, :121-129). */
+cpb_status cpb_bowe_hopwood_crh_batch(cpb_bowe_hopwood_ctx* ctx, const uint8_t* in, size_t len, size_t stride, uint64_t* out_x, size_t n);
+cpb_status cpb_bowe_hopwood_crh_batch_dev(cpb_bowe_hopwood_ctx* ctx, const uint8_t* in, size_t len, size_t stride, uint64_t* out_x,
+                                          size_t n, void* stream);
+/* n x bowe_hopwood::TwoToOneCRH::compress (mod.rs:228-240): children_x = n x (left, right) base-field elements,
+ * serialised (32-byte LE canonical each) into the zeroed window_size*num_windows/8-byte buffer of `evaluate`
+ * (mod.rs:200-226).  The _dev form needs cpb_bowe_hopwood_two_to_one_scratch_bytes(ctx, n) bytes of device scratch. */
+cpb_status cpb_bowe_hopwood_two_to_one_batch(cpb_bowe_hopwood_ctx* ctx, const uint64_t* children_x, uint64_t* out_x, size_t n);
+cpb_status cpb_bowe_hopwood_two_to_one_batch_dev(cpb_bowe_hopwood_ctx* ctx, const uint64_t* children_x, uint64_t* out_x, size_t n,
+                                                 void* scratch, void* stream);
+size_t cpb_bowe_hopwood_two_to_one_scratch_bytes(const cpb_bowe_hopwood_ctx* ctx, size_t n);
 
 /* ---- Merkle tree, byte leaves -------------------------------------------------------------- */
 /* MerkleTree::new for Config{Leaf=[u8], LeafHash=pedersen::CRH, LeafInnerDigestConverter=

@@ -59,6 +59,8 @@ def lib():
         L.oref_pedersen_merkle.restype = C.c_int
         L.oref_mixed_merkle.argtypes = [C.c_void_p, C.c_void_p, u8p, C.c_size_t, C.c_size_t, u64p, u64p, C.c_int]
         L.oref_mixed_merkle.restype = C.c_int
+        L.oref_bowe_hopwood_batch.argtypes = [C.c_void_p, u8p, C.c_size_t, C.c_size_t, u64p, C.c_size_t, C.c_int]
+        L.oref_bowe_hopwood_batch.restype = C.c_int
         _lib = L
     return _lib
 
@@ -199,6 +201,15 @@ class Pedersen:
         rc = lib().oref_pedersen_batch(self.h, _b(inputs), ln, ln, r, _p(out), n, threads)
         if rc:
             raise ValueError("incorrect input length")
+        return out
+
+    def bowe_hopwood_batch(self, inputs: np.ndarray, threads: int = 1) -> np.ndarray:
+        """Bowe-Hopwood CRH over these generators (window_size = chunks per segment): (n, len) uint8 -> (n, 4) x-coordinates."""
+        inputs = np.ascontiguousarray(inputs, dtype=np.uint8)
+        n, ln = inputs.shape
+        out = np.empty((n, 4), dtype=np.uint64)
+        if lib().oref_bowe_hopwood_batch(self.h, _b(inputs), ln, ln, _p(out), n, threads):
+            raise ValueError("incorrect input bitlength")
         return out
 
     def compress_batch(self, children: np.ndarray, threads: int = 1) -> np.ndarray:

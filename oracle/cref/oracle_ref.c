@@ -545,3 +545,49 @@ int oref_mixed_merkle(const pedersen_t *leafP, const poseidon_t *nodeP, const ui
     }
     return 0;
 }
+
+/* ---------------------------------------------------------------- Bowe-Hopwood Pedersen CRH */
+
+/* bowe_hopwood::CRH::evaluate (R/crh/bowe_hopwood/mod.rs:115-185) over the generators of a pedersen_t
+ * (generators[w][j] flattened; window_size = chunks per segment).  Output: x-coordinate (Montgomery).
+ * Returns 1 for "incorrect input bitlength" (:121-129). */
+static int bh_one(const pedersen_t *P, const uint8_t *in, size_t len, fe *ox) {
+    if (len * 8 > P->n_gens * 3) return 1;
+    size_t nbits = len * 8, nchunks = (nbits + 2) / 3;                  /* padded to a multiple of 3 with zeros (:133-140) */
+    te_point acc;
+    te_identity(P, &acc);
+    for (size_t k = 0; k < nchunks && k < P->n_gens; k++) {             /* chunk k <-> generators[k / WS][k % WS] */
+        int c[3];
+        for (int b = 0; b < 3; b++) {
+            size_t bit = 3 * k + b;
+            c[b] = bit < nbits ? (in[bit >> 3] >> (bit & 7)) & 1 : 0;
+        }
+        /* encoded = g (+ g if c0) (+ 2g if c1), negated if c2 (:165-177) */
+        te_point enc;
+        te_identity(P, &enc);
+        int mult = 1 + c[0] + 2 * c[1];
+        for (int r = 0; r < mult; r++) te_add_affine(P, &enc, &P->gx[k], &P->gy[k]);
+        fe ex, ey;
+        te_to_affine(P, &enc, &ex, &ey);
+        if (c[2]) { fe z; memset(&z, 0, sizeof z); fe_sub(&P->F, &ex, &z, &ex); }
+        te_add_affine(P, &acc, &ex, &ey);
+    }
+    fe y;
+    te_to_affine(P, &acc, ox, &y);
+    return 0;
+}
+
+typedef struct { const pedersen_t *P; const uint8_t *in; size_t len, stride; u64 *out; int err; } bh_job;
+static void bh_range(void *c, size_t b, size_t e) {
+    bh_job *j = (bh_job *)c;
+    for (size_t i = b; i < e; i++) {
+        fe x;
+        if (bh_one(j->P, j->in + i * j->stride, j->len, &x)) { j->err = 1; return; }
+        memcpy(j->out + 4 * i, x.l, 32);
+    }
+}
+int oref_bowe_hopwood_batch(const pedersen_t *P, const uint8_t *in, size_t len, size_t stride, u64 *out_x, size_t n, int threads) {
+    bh_job j = {P, in, len, stride, out_x, 0};
+    parallel_for(n, threads, bh_range, &j);
+    return j.err;
+}
