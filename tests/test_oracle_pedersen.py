@@ -69,3 +69,22 @@ def test_c_pedersen_merkle_small():
     n2 = PD.two_to_one_compress(prm, W, d[2], d[3])
     root = PD.two_to_one_compress(prm, W, n1, n2)
     assert [tuple(cref.mont_to_ints(x, jj.Q)) for x in nn] == [root, n1, n2]
+
+
+def test_bowe_hopwood_c_equals_python_and_encoding():
+    """R/crh/bowe_hopwood/mod.rs:115-185: chunk value v -> (1 + c0 + 2*c1) * (-1)^c2 times its generator; only covered
+    chunks contribute; the two restatements agree."""
+    from oracle import bowe_hopwood as OBH
+    w = PD.Window(63, 2)
+    prm = OBH.setup(w, 3)
+    g = prm.generators[0]
+    for v, e in ((0, 1), (1, 2), (2, 3), (3, 4), (4, -1), (5, -2), (6, -3), (7, -4)):
+        pt = jj.add(jj.add(jj.mul(e % jj.ORDER, g[0]), g[1]), g[2])          # a 1-byte input covers chunks 0, 1, 2
+        assert OBH.crh_evaluate(prm, w, bytes([v])) == pt[0]
+    assert OBH.crh_evaluate(prm, w, b"") == 0
+    c = cref.Pedersen(prm, w)
+    for ln in (0, 1, 20, 47):
+        inp = np.ascontiguousarray(cref.synth_bytes(5 + ln, 3 * max(ln, 1)).reshape(3, max(ln, 1))[:, :ln])
+        out = c.bowe_hopwood_batch(inp)
+        for i in range(3):
+            assert cref.mont_to_ints(out[i], jj.Q)[0] == OBH.crh_evaluate(prm, w, bytes(inp[i]))
