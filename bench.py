@@ -33,6 +33,11 @@ WORKLOADS = {
     "merkle_2^24_poseidon_bn254": ("bn254", 24, 2, "2^24-leaf Poseidon Merkle tree, BN254 Fr (t=3, RF=8, RP=57, alpha=5), 2-element leaves"),
     "merkle_2^20_poseidon_bls12_381": ("bls", 20, 2, "2^20-leaf Poseidon Merkle tree, BLS12-381 Fr default rate-2 (alpha=17, RF=8, RP=31)"),
 }
+# parity-test configurations that can also be timed (single GPU only; not the contract line)
+EXTRA_WORKLOADS = {
+    "pedersen_crh_2^20_jubjub": "BASELINE config 3: 2^20 x 128-byte Pedersen CRH + commitment, Jubjub, window 4x256",
+    "mixed_merkle_2^22": "BASELINE config 5 shape on one GPU: 2^22 x 128-byte leaves, Pedersen leaf hash (x-coordinate) + Poseidon two-to-one over BLS12-381 Fr",
+}
 DEFAULT_WORKLOAD = "merkle_2^24_poseidon_bn254"
 HBM_PEAK_FALLBACK = 6650.0      # GB/s, B200_PROFILING.md fallback
 
@@ -328,15 +333,79 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_extra(args):
+    """Device-resident timing of the Pedersen / mixed-tree configurations (one GPU)."""
+    import numpy as np
+    import torch
+    import crypto_primitives_b200 as cp
+    from crypto_primitives_b200 import _native as N
+    from crypto_primitives_b200.commitment.pedersen import Commitment
+    from crypto_primitives_b200.crh.pedersen import Window
+
+    class Rng:
+        def __init__(self, seed): self.g = np.random.default_rng(seed)
+        def field(self, q): return int.from_bytes(self.g.bytes(40), "little") % q
+
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda:0")
+    prm = Commitment.setup(Rng(0xB2000003), Window(4, 256))
+    ctx = prm.context(0)
+    st = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        ts = []
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    g = torch.Generator(device="cpu").manual_seed(3)
+    if args.workload == "pedersen_crh_2^20_jubjub":
+        n = 1 << 20
+        inp = torch.randint(0, 256, (n, 128), dtype=torch.uint8, generator=g).to(dev)
+        rnd = torch.randint(0, 256, (n, 32), dtype=torch.uint8, generator=g)
+        rnd[:, 31] &= 0x0F
+        rnd = rnd.to(dev)
+        out = torch.empty((n, 2, 4), dtype=torch.int64, device=dev)
+        ms_crh = timed(lambda: N.check(N.lib.cpb_pedersen_crh_batch_dev(ctx, inp.data_ptr(), 128, 128, out.data_ptr(), n, st)))
+        ms_com = timed(lambda: N.check(N.lib.cpb_pedersen_commit_batch_dev(ctx, inp.data_ptr(), 128, 128, rnd.data_ptr(), out.data_ptr(), n, st)))
+        line = {"metric": "pedersen_hashes_per_sec", "value": n / (ms_crh * 1e-3), "unit": "hashes/s", "ms_per_step": ms_crh,
+                "commit_per_sec": n / (ms_com * 1e-3), "commit_ms": ms_com}
+    else:
+        n = 1 << 22
+        node = poseidon_params(cp, "bls")
+        nctx = node.context(0)
+        leaves = torch.randint(0, 256, (n, 128), dtype=torch.uint8, generator=g).to(dev)
+        ln = torch.empty((n, 4), dtype=torch.int64, device=dev)
+        nn = torch.empty((n - 1, 4), dtype=torch.int64, device=dev)
+        ms = timed(lambda: N.check(N.lib.cpb_merkle_mixed_build_dev(ctx, nctx, leaves.data_ptr(), 128, 128, n, ln.data_ptr(), nn.data_ptr(), st)))
+        line = {"metric": "mixed_merkle_build_s", "value": ms * 1e-3, "unit": "s", "ms_per_step": ms, "higher_is_better": False,
+                "hashes_per_step": {"pedersen": n, "poseidon": n - 1}}
+    line.update({"n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "data": "synthetic", "dtype": "u32x8 (256-bit Montgomery integer)",
+                 "config": {"workload": args.workload, "description": EXTRA_WORKLOADS[args.workload], "l2": "flushed between timed steps"}})
+    line.setdefault("higher_is_better", True)
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + list(EXTRA_WORKLOADS))
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload in EXTRA_WORKLOADS:
+        if args.impl != "b200" or args.gpus != 1:
+            raise SystemExit("the extra workloads are single-GPU, --impl b200 only")
+        run_extra(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
