@@ -12,7 +12,10 @@ namespace cpb {
 
 constexpr int kBlock = 128;
 // resident CTAs per SM the register allocator must allow: 5 for the narrow states (96 registers), 1 for wide ones
-constexpr int pos_min_blocks(int t) { return t <= 3 ? 5 : t <= 5 ? 3 : 1; }
+#ifndef CPB_POS_MINB3
+#define CPB_POS_MINB3 5
+#endif
+constexpr int pos_min_blocks(int t) { return t <= 3 ? CPB_POS_MINB3 : t <= 5 ? 3 : 1; }
 
 template <class F, int T>
 __global__ void __launch_bounds__(kBlock, pos_min_blocks(T))
