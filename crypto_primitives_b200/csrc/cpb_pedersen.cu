@@ -455,6 +455,19 @@ extern "C" int cpb_poseidon_ctx_device(const cpb_poseidon_ctx* ctx);
 
 namespace {
 
+
+// The hash launchers take their projective scratch from the device's stream-ordered pool.  By default that pool
+// returns memory to the OS at every synchronisation, which makes the next cudaMallocAsync re-map 128 B x n each call;
+// keep the memory cached in the pool instead.
+void keep_pool_memory(int device) {
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+}
+
 struct CurveInfo {
     int field_id;
     bool d_is_ratio;      // d = -(num/den) when true, else d = num
@@ -625,6 +638,7 @@ cpb_status cpb_pedersen_ctx_create_ex(int curve_id, int window_size, int num_win
     CPB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
     if (major != 10) return fail(CPB_NO_DEVICE, "device %d is sm_%d0; this library is built for sm_100a only", device, major);
 
+    keep_pool_memory(device);
     cpb_pedersen_ctx* c = new cpb_pedersen_ctx();
     c->curve_id = curve_id; c->field_id = ci.field_id; c->device = device; c->sms = sm_count(device);
     c->window_size = window_size; c->num_windows = num_windows; c->n_rand = (int)n_rand; c->nbits = nbits;
@@ -938,6 +952,7 @@ cpb_status cpb_bowe_hopwood_ctx_create(int curve_id, int window_size, int num_wi
     CPB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
     if (major != 10) return fail(CPB_NO_DEVICE, "device %d is sm_%d0; this library is built for sm_100a only", device, major);
 
+    keep_pool_memory(device);
     cpb_bowe_hopwood_ctx* c = new cpb_bowe_hopwood_ctx();
     c->curve_id = curve_id; c->field_id = ci.field_id; c->device = device; c->sms = sm_count(device);
     c->window_size = window_size; c->num_windows = num_windows; c->n_gens = n_gens;

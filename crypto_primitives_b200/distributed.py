@@ -79,6 +79,34 @@ class CudaPoseidonBackend:
         return nodes
 
 
+class CudaMixedBackend(CudaPoseidonBackend):
+    """BASELINE config 5: byte leaves hashed with PedersenCRHCompressor (x-coordinate, R/crh/injective_map/mod.rs:22-62),
+    inner nodes with poseidon::TwoToOneCRH over the curve's base field.  local_leaves: (n, leaf_len) uint8 on the GPU."""
+
+    def __init__(self, pedersen_params, node_params, device_index: int):
+        from . import _native as N
+        self.N = N
+        self.dev = device_index
+        self.leaf_ctx = pedersen_params.context(device_index)
+        self.node_ctx = node_params.context(device_index)
+        self._ws = {}
+
+    def build_local(self, leaves: torch.Tensor):
+        n, ln = leaves.shape
+        leaf_nodes = self._buf("leaf", (n, 4), leaves.device)
+        nodes = self._buf("nodes", (n - 1, 4), leaves.device)
+        self.N.check(self.N.lib.cpb_merkle_mixed_build_dev(self.leaf_ctx, self.node_ctx, leaves.data_ptr(), ln, leaves.stride(0), n,
+                                                           leaf_nodes.data_ptr(), nodes.data_ptr(), self._stream()))
+        return leaf_nodes, nodes
+
+    def hash_leaves(self, leaves: torch.Tensor):
+        n, ln = leaves.shape
+        out = self._buf("leaf", (n, 4), leaves.device)
+        self.N.check(self.N.lib.cpb_pedersen_crh_x_batch_dev(self.leaf_ctx, leaves.data_ptr(), ln, leaves.stride(0), out.data_ptr(), n,
+                                                             self._stream()))
+        return out
+
+
 @dataclass
 class ShardedTree:
     """Result of a sharded build on this rank."""
