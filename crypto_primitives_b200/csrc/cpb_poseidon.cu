@@ -84,6 +84,10 @@ CPB_POS_WIDTHS(CPB_POS_EXTERN, Bls12_381_Fr)
 CPB_POS_WIDTHS(CPB_POS_EXTERN, Bn254_Fr)
 CPB_POS_WIDTHS(CPB_POS_EXTERN, Jubjub_Fr)
 CPB_POS_WIDTHS(CPB_POS_EXTERN, Bls12_377_Fr)
+CPB_POS_EXTERN_TEAM(Bls12_381_Fr)
+CPB_POS_EXTERN_TEAM(Bn254_Fr)
+CPB_POS_EXTERN_TEAM(Jubjub_Fr)
+CPB_POS_EXTERN_TEAM(Bls12_377_Fr)
 }  // namespace cpb
 
 namespace {
@@ -113,8 +117,27 @@ PoseidonDev to_dev(const host::PoseidonSchedule& S) {
         case CPB_BLS12_377_FR: CPB_FOR_T(Bls12_377_Fr, M, __VA_ARGS__)               \
     }
 
+// Largest batch of two-to-one hashes sent to the three-warp team kernel: beyond ~6000 hashes the GPU's 592 warp
+// schedulers are all busy with one hash per thread anyway.  CPB_TEAM_MAX overrides (0 disables).
+size_t team_max() {
+    static long v = -1;
+    if (v < 0) {
+        const char* e = getenv("CPB_TEAM_MAX");
+        v = e ? atol(e) : 4096;
+    }
+    return (size_t)v;
+}
+
 cpb_status launch_crh(cpb_poseidon_ctx* c, const u32* in, size_t len, u32* out, size_t n, cudaStream_t st, size_t n_out = 1) {
     if (n == 0 || n_out == 0) return CPB_OK;
+    if (c->dev.t == 3 && c->dev.cap == 1 && len == 2 && n_out == 1 && n <= team_max()) {
+        switch (c->field_id) {
+            case CPB_BLS12_381_FR: return launch_team_f<Bls12_381_Fr>(c, in, out, n, st);
+            case CPB_BN254_FR: return launch_team_f<Bn254_Fr>(c, in, out, n, st);
+            case CPB_JUBJUB_FR: return launch_team_f<Jubjub_Fr>(c, in, out, n, st);
+            case CPB_BLS12_377_FR: return launch_team_f<Bls12_377_Fr>(c, in, out, n, st);
+        }
+    }
     CPB_FOR_FIELD(launch_crh_ft, c, in, len, out, n_out, n, st)
     return fail(CPB_UNSUPPORTED, "state width t=%d is not built (this library: t = 2..9)", c->dev.t);
 }

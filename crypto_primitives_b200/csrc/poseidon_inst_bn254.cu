@@ -2,4 +2,5 @@
 #include "poseidon_kernels.cuh"
 namespace cpb {
 CPB_POS_WIDTHS(CPB_POS_INSTANTIATE, Bn254_Fr)
+CPB_POS_INSTANTIATE_TEAM(Bn254_Fr)
 }

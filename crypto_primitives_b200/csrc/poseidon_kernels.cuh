@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "poseidon.cuh"
 #include "poseidon_host.hpp"
+#include "poseidon_team.cuh"
 
 namespace cpb {
 
@@ -148,6 +149,55 @@ cpb_status launch_verify_ft(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, cons
     return CPB_OK;
 }
 
+// Three warps per 32 two-to-one hashes (poseidon_team.cuh); t = 3, capacity 1 only.
+template <class F>
+__global__ void __launch_bounds__(96)
+k_poseidon_compress_team(PoseidonDev P, const u32* __restrict__ consts, const u32* __restrict__ pairs, u32* __restrict__ out, long n) {
+    extern __shared__ __align__(16) u32 cs[];
+    __shared__ __align__(8) unsigned long long mbar;
+    tma_stage_to_smem(cs, consts, (unsigned)P.n_elems * 32u, &mbar);
+    u32* xb = cs + 8 * P.n_elems;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32* ct = cs + (int)threadIdx.x * P.zero;
+    u32 pm[8];
+    ld_elem(pm, ct + 8 * P.off_mod);
+    int top_bit = 0;
+    for (int i = 63; i > 0; i--)
+        if ((P.alpha >> i) & 1) { top_bit = i; break; }
+    const int total = P.rf + P.rp;
+    const long nblk = (n + 31) / 32;
+    for (long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const long i = blk * 32 + lane;
+        const bool active = i < n;
+        const long ii = active ? i : n - 1;
+        u32 s[8];
+        if (w == 0) fp_zero(s);
+        else ld_elem(s, pairs + 16 * ii + 8 * (w - 1));
+#pragma unroll 1
+        for (int r = 0; r < total; r++) {
+            team_phase_a<F>(s, w, lane, r, P, ct, pm, xb, top_bit);
+            __syncthreads();
+            team_phase_b<F>(s, w, lane, r, P, ct, pm, xb);
+        }
+        if (w == 1 && active) st_elem(out + 8 * i, s);
+        __syncthreads();                                   // the exchange buffers are reused by the next 32 hashes
+    }
+}
+
+template <class F>
+cpb_status launch_team_f(cpb_poseidon_ctx* c, const u32* pairs, u32* out, size_t n, cudaStream_t st) {
+    size_t smem = (size_t)c->dev.n_elems * 32 + (size_t)kTeamXbWords * 4;
+    static thread_local const void* configured = nullptr;
+    if (smem > 48 * 1024 && configured != (const void*)k_poseidon_compress_team<F>) {
+        CPB_CUDA(cudaFuncSetAttribute(k_poseidon_compress_team<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = (const void*)k_poseidon_compress_team<F>;
+    }
+    long nblk = ((long)n + 31) / 32;
+    k_poseidon_compress_team<F><<<(int)nblk, 96, smem, st>>>(c->dev, c->d_consts, pairs, out, (long)n);
+    CPB_CUDA(cudaGetLastError());
+    return CPB_OK;
+}
+
 // explicit instantiations live in poseidon_inst_<field>.cu
 #define CPB_POS_WIDTHS(M, F) M(F, 2) M(F, 3) M(F, 4) M(F, 5) M(F, 6) M(F, 7) M(F, 8) M(F, 9)
 #define CPB_POS_INSTANTIATE(F, T)                                                                                        \
@@ -155,6 +205,8 @@ cpb_status launch_verify_ft(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, cons
     template cpb_status launch_permute_ft<F, T>(cpb_poseidon_ctx*, const u32*, u32*, size_t, cudaStream_t);             \
     template cpb_status launch_verify_ft<F, T>(cpb_poseidon_ctx*, cpb_poseidon_ctx*, const u32*, const u32*, size_t, const u32*, \
                                                const u32*, int, const unsigned long long*, unsigned char*, size_t, cudaStream_t);
+#define CPB_POS_INSTANTIATE_TEAM(F) template cpb_status launch_team_f<F>(cpb_poseidon_ctx*, const u32*, u32*, size_t, cudaStream_t);
+#define CPB_POS_EXTERN_TEAM(F) extern template cpb_status launch_team_f<F>(cpb_poseidon_ctx*, const u32*, u32*, size_t, cudaStream_t);
 #define CPB_POS_EXTERN(F, T)                                                                                             \
     extern template cpb_status launch_crh_ft<F, T>(cpb_poseidon_ctx*, const u32*, size_t, u32*, size_t, size_t, cudaStream_t);     \
     extern template cpb_status launch_permute_ft<F, T>(cpb_poseidon_ctx*, const u32*, u32*, size_t, cudaStream_t);      \

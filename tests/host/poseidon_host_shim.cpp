@@ -2,9 +2,10 @@
 // PTX primitives emulated) driven by the product's own host-side schedule derivation
 // (poseidon_host.hpp).  Lets tests/test_poseidon_host.py check, without a GPU, that the sparse
 // round schedule + device permutation reproduce the oracle bit-for-bit.  Not part of the product.
-#include "../../crypto_primitives_b200/csrc/poseidon.cuh"
+#include "../../crypto_primitives_b200/csrc/poseidon_team.cuh"
 #include "../../crypto_primitives_b200/csrc/poseidon_host.hpp"
 #include <cstring>
+#include <vector>
 using namespace cpb;
 
 static PoseidonDev to_dev(const host::PoseidonSchedule& S) {
@@ -131,4 +132,45 @@ extern "C" int host_poseidon_verify(int field, int rate, int cap, int rf, int rp
         run_verify<Jubjub_Fr, 3>(D, cs, (const u32*)root, (const u32*)leaves, leaf_len, (const u32*)sib, (const u32*)paths, plen, idx, ok, n);
     else return -1;
     return 0;
+}
+
+// CPU model of the three-warp team kernel (poseidon_team.cuh): phases run for w = 0, 1, 2 in sequence per round.
+template <class F> static void run_team(const PoseidonDev& D, const u32* cs, const u32* pairs, long n, u32* out) {
+    u32 pm[8];
+    ld_elem(pm, cs + 8 * D.off_mod);
+    int top_bit = 0;
+    for (int i = 63; i > 0; i--) if ((D.alpha >> i) & 1) { top_bit = i; break; }
+    std::vector<u32> xb(kTeamXbWords, 0xdeadbeefu);
+    for (long i = 0; i < n; i++) {
+        u32 s[3][8];
+        fp_zero(s[0]);
+        for (int j = 0; j < 8; j++) { s[1][j] = pairs[16 * i + j]; s[2][j] = pairs[16 * i + 8 + j]; }
+        const int lane = (int)(i & 31);
+        for (int r = 0; r < D.rf + D.rp; r++) {
+            for (int w = 0; w < 3; w++) team_phase_a<F>(s[w], w, lane, r, D, cs, pm, xb.data(), top_bit);
+            for (int w = 0; w < 3; w++) team_phase_b<F>(s[w], w, lane, r, D, cs, pm, xb.data());
+        }
+        for (int j = 0; j < 8; j++) out[8 * i + j] = s[1][j];
+    }
+}
+extern "C" int host_poseidon_team_compress(int field, int rf, int rp, unsigned long long alpha, const uint64_t* ark, const uint64_t* mds,
+                                           int allow_sparse, const uint64_t* pairs, long n, uint64_t* out) {
+    host::Field F(host::field_modulus(field));
+    host::PoseidonParams P;
+    P.rate = 2; P.capacity = 1; P.full_rounds = rf; P.partial_rounds = rp; P.alpha = alpha;
+    P.ark.resize((size_t)(rf + rp) * 3);
+    P.mds.resize(9);
+    memcpy(P.ark.data(), ark, P.ark.size() * 32);
+    memcpy(P.mds.data(), mds, P.mds.size() * 32);
+    host::PoseidonSchedule S = host::derive_schedule(F, P, allow_sparse != 0);
+    PoseidonDev D = to_dev(S);
+    const u32* cs = reinterpret_cast<const u32*>(S.consts.data());
+    switch (field) {
+        case 0: run_team<Bls12_381_Fr>(D, cs, (const u32*)pairs, n, (u32*)out); break;
+        case 1: run_team<Bn254_Fr>(D, cs, (const u32*)pairs, n, (u32*)out); break;
+        case 2: run_team<Jubjub_Fr>(D, cs, (const u32*)pairs, n, (u32*)out); break;
+        case 3: run_team<Bls12_377_Fr>(D, cs, (const u32*)pairs, n, (u32*)out); break;
+        default: return -1;
+    }
+    return S.sparse;
 }

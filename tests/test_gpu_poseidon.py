@@ -158,3 +158,15 @@ def test_sponge_surface_matches_oracle_state_machine():
         o3.absorb(ints[3 * i:3 * i + 3])
         assert f.to_ints(got[i]) == o3.squeeze_native_field_elements(5)
     assert np.array_equal(absorb_squeeze_batch(cfg, x, 1)[:, 0], CRH.evaluate_batch(cfg, x))
+
+
+@pytest.mark.parametrize("which", ALL_CONFIGS)
+def test_small_batches_use_the_team_kernel(which):
+    """Two-to-one batches of <= 4096 hashes (the latency-bound top of a Merkle tree) go through the three-warp team
+    kernel (csrc/poseidon_team.cuh); ragged sizes around the 32-hash CTA granularity, against the oracle."""
+    _, ocfg = oracle_config(which)
+    cfg = product_config(which)
+    O = cref.Poseidon(ocfg)
+    for n in (1, 31, 32, 33, 1000, 4096, 4097):
+        pairs = synth_elems(4000 + n, (n, 2), ocfg.p)
+        assert np.array_equal(TwoToOneCRH.compress_batch(cfg, pairs), O.compress_batch(pairs, threads=8)), (which, n)

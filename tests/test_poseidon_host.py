@@ -145,3 +145,21 @@ def test_path_verification_device_code(shim):
     swapped = idx.copy(); swapped[[0, 1]] = swapped[[1, 0]]
     r = run(root, swapped)
     assert not r[0] and not r[1] and r[2:].all()                                            # wrong position
+
+
+@pytest.mark.parametrize("which", ALL_CONFIGS)
+def test_three_warp_team_schedule(shim, which):
+    """CPU model of the latency-oriented team kernel (csrc/poseidon_team.cuh: one warp per state lane, lanes exchanged
+    through a double-buffered array) == the oracle's two-to-one compression, sparse and dense schedules."""
+    fname, cfg = oracle_config(which)
+    p = cfg.p
+    ark = cref.ints_to_mont([x for r in cfg.ark for x in r], p)
+    mds = cref.ints_to_mont([x for r in cfg.mds for x in r], p)
+    pairs = synth_elems(71, (40, 2), p)
+    pairs[0] = cref.ints_to_mont([p - 1, p - 1], p)
+    exp = cref.Poseidon(cfg).compress_batch(pairs)
+    for sp in (1, 0):
+        out = np.zeros((40, 4), dtype=np.uint64)
+        rc = shim.host_poseidon_team_compress(FID[fname], cfg.full_rounds, cfg.partial_rounds, C.c_ulonglong(cfg.alpha), _P(ark), _P(mds), sp,
+                                              _P(np.ascontiguousarray(pairs)), C.c_long(40), _P(out))
+        assert rc == sp and np.array_equal(out, exp), (which, sp)
