@@ -98,14 +98,18 @@ def get_default_poseidon_parameters(field: Field, rate: int, optimized_for_weigh
     return PoseidonConfig(field, rf.value, rp.value, alpha.value, mds, ark, rate, 1)
 
 
+FULL = "Full"        # FieldElementSize::Full; an int is FieldElementSize::Truncated(bits) (R/sponge/mod.rs:24-36)
+
+
 class PoseidonSponge:
     """Duplex sponge over the GPU permutation -- host mirror of PoseidonSponge<F> (R/sponge/poseidon/mod.rs:47-63):
     CryptographicSponge::{new, absorb, squeeze_bytes, squeeze_bits, squeeze_field_elements} (mod.rs:220-321) and
     FieldBasedCryptographicSponge::squeeze_native_field_elements (mod.rs:323-345), with the same mode bookkeeping
-    (absorb_internal / squeeze_internal, mod.rs:124-186).  Only native field elements can be absorbed (the `Fp` and
-    `&[Fp]` Absorb impls, R/sponge/absorb.rs:154-167, 284-292).  Every permutation is one GPU call of batch size 1:
-    correct but slow -- a single transcript is sequential by nature; for many independent sponges use
-    `absorb_squeeze_batch`."""
+    (absorb_internal / squeeze_internal, mod.rs:124-186), `fork` (R/sponge/mod.rs:145-153), the sized squeezes
+    (R/sponge/mod.rs:57-96,170-187) and SpongeExt::{from_state, into_state} (mod.rs:347-370).  `absorb` takes native
+    field elements as (k, 4) Montgomery limbs or any value sponge/absorb.py can encode (R/sponge/absorb.rs).  Every
+    permutation is one GPU call of batch size 1: correct but slow -- a single transcript is sequential by nature; for
+    many independent sponges use `absorb_squeeze_batch`."""
 
     def __init__(self, parameters: PoseidonConfig, device: int = 0):
         self.parameters = parameters
@@ -163,9 +167,33 @@ class PoseidonSponge:
             rate_start = 0
 
     # -- public surface
+    def clone(self) -> "PoseidonSponge":
+        c = PoseidonSponge(self.parameters, self.device)
+        c.state, c.mode = self.state.copy(), self.mode
+        return c
+
+    @classmethod
+    def from_state(cls, state, parameters: PoseidonConfig, device: int = 0):   # mod.rs:357-362
+        s = cls(parameters, device)
+        s.state, s.mode = np.array(state[0], dtype=np.uint64).reshape(-1, 4), state[1]
+        return s
+
+    def into_state(self):                                                       # mod.rs:364-369
+        return (self.state, self.mode)
+
+    def fork(self, domain: bytes) -> "PoseidonSponge":
+        """R/sponge/mod.rs:145-153: clone, then absorb usize(len(domain)) bytes || domain as one byte string."""
+        new = self.clone()
+        new.absorb(len(domain).to_bytes(8, "little") + bytes(domain))
+        return new
+
     def absorb(self, elems):
-        """elems: (k, 4) Montgomery limbs (or a single (4,) element)."""
-        e = np.asarray(elems, dtype=np.uint64).reshape(-1, 4)
+        """elems: (k, 4) Montgomery limbs (or a single (4,) element), or any absorbable of sponge/absorb.py."""
+        if isinstance(elems, np.ndarray):
+            e = np.asarray(elems, dtype=np.uint64).reshape(-1, 4)
+        else:
+            from .absorb import to_sponge_field_elements
+            e = to_sponge_field_elements(elems, self.parameters.field)
         if e.shape[0] == 0:
             return
         kind, idx = self.mode
@@ -187,7 +215,39 @@ class PoseidonSponge:
             idx = 0
         return self._squeeze_internal(idx, num_elements)
 
-    squeeze_field_elements = squeeze_native_field_elements       # the native TypeId fast path, mod.rs:309-315
+    def squeeze_field_elements(self, num_elements: int, field: Field | None = None) -> np.ndarray:
+        """mod.rs:309-320: the native fast path, else `num_elements` Full-size elements of `field`."""
+        if field is None or field.id == self.parameters.field.id:
+            return self.squeeze_native_field_elements(num_elements)
+        return self.squeeze_field_elements_with_sizes([FULL] * num_elements, field)
+
+    def squeeze_native_field_elements_with_sizes(self, sizes) -> np.ndarray:
+        """R/sponge/mod.rs:170-187.  sizes: FULL or an int bit count (FieldElementSize::Truncated)."""
+        return self.squeeze_field_elements_with_sizes(sizes, None)
+
+    def squeeze_field_elements_with_sizes(self, sizes, field: Field | None = None) -> np.ndarray:
+        """mod.rs:291-307 over R/sponge/mod.rs:57-96: (len(sizes), 4) Montgomery limbs of `field` (default: native)."""
+        native = self.parameters.field
+        field = native if field is None else field
+        sizes = list(sizes)
+        if not sizes:
+            return np.zeros((0, 4), dtype=np.uint64)
+        if field.modulus == native.modulus and all(s == FULL for s in sizes):
+            return self.squeeze_native_field_elements(len(sizes))
+        widths = []
+        for s in sizes:
+            if s == FULL:
+                widths.append(field.modulus_bit_size - 1)
+            elif s > field.modulus_bit_size:
+                raise ValueError("num_bits is greater than the capacity of the field.")   # R/sponge/mod.rs:39-42
+            else:
+                widths.append(int(s))
+        bits = self.squeeze_bits(sum(widths))
+        vals, pos = [], 0
+        for w in widths:
+            vals.append(sum(1 << i for i, b in enumerate(bits[pos:pos + w]) if b))
+            pos += w
+        return field.elements(vals)
 
     def squeeze_bytes(self, num_bytes: int) -> bytes:
         """mod.rs:259-274."""

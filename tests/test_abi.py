@@ -67,3 +67,19 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(N.CpbError) as e:
         cp.crh_poseidon.CRH.evaluate(cfg, cp.BLS12_381_FR.elements([0, 1, 2]))
     assert e.value.status in (N.CPB_NO_DEVICE, N.CPB_CUDA_ERROR)
+
+
+def test_absorb_encodings_host_side():
+    """sponge/absorb.py is pure host logic (R/sponge/absorb.rs): checked here against the oracle's restatement without a GPU
+    (only cpb_field_modulus, a host function of the library, is called)."""
+    import crypto_primitives_b200 as cp
+    from crypto_primitives_b200.sponge import absorb as A
+    from oracle import absorb as OA
+    f = cp.BLS12_381_FR
+    p = f.modulus
+    pairs = [([1, -2, 3], [1, -2, 3]), (bytes(range(64)), bytes(range(64))), ("str", "str"), (None, None), (False, False),
+             (A.Some(A.usize(5)), OA.Some(OA.UInt(5, 64))), (A.WithLength(b"abc"), OA.WithLength(b"abc")),
+             (A.Elems(f, f.elements([5, p - 1])), [OA.Fe(5, p), OA.Fe(p - 1, p)]), (A.UInt(2**127, 128), OA.UInt(2**127, 128))]
+    for g, o in pairs:
+        assert A.to_sponge_bytes(g) == OA.to_sponge_bytes(o)
+        assert f.to_ints(A.to_sponge_field_elements(g, f)) == OA.to_sponge_field_elements(o, p)

@@ -116,6 +116,10 @@ def test_commitment_matches_oracle(ws, nw, ln):
     assert np.array_equal(Commitment.commit(prm, bytes(inp[7]), rs[7]), exp[7])
     # commit with r = 0 is the plain CRH of the padded input
     assert np.array_equal(exp[0], CRH.evaluate_batch(prm, inp[:1])[0])
+    # PedersenCommCompressor<_, TECompressor, _> (R/commitment/injective_map/mod.rs:11-44): the x-coordinate
+    from crypto_primitives_b200.commitment.injective_map import PedersenCommCompressor
+    assert np.array_equal(PedersenCommCompressor.commit_batch(prm, inp, rb), exp[:, 0, :])
+    assert np.array_equal(PedersenCommCompressor.commit(prm, bytes(inp[9]), rs[9]), exp[9, 0])
     with pytest.raises(ValueError):
         Commitment.commit_batch(prm, np.zeros((1, ws * nw // 8 + 1), dtype=np.uint8), rb[:1])
 
