@@ -61,6 +61,16 @@ def test_multiproof_prefix_lengths_kat():
     tree = MerkleTree.new(cfg, cfg, synth_elems(4, (8, 2), ocfg.p))
     mp = tree.generate_multi_proof(range(8))
     assert mp.auth_paths_prefix_lenghts == kats()["multiproof_prefix_lengths_8_leaves"]["value"]
+    # proofs survive the wire format (crypto_primitives_b200/serialize.py) and still verify against the GPU-built root
+    from crypto_primitives_b200 import serialize as S
+    codec = S.FieldDigest(cfg.field)
+    leaves = synth_elems(4, (8, 2), ocfg.p)
+    mp2 = S.de_multipath(S.ser_multipath(mp, codec), codec)
+    assert mp2.verify(cfg, cfg, tree.root(), leaves)
+    p5 = S.de_path(S.ser_path(tree.generate_proof(5), codec), codec)
+    assert p5.verify(cfg, cfg, tree.root(), leaves[5]) and not p5.verify(cfg, cfg, tree.root(), leaves[4])
+    cfg2 = S.de_poseidon_config(cfg.field, S.ser_poseidon_config(cfg))
+    assert np.array_equal(MerkleTree.new(cfg2, cfg2, leaves).root(), tree.root())
 
 
 def test_blank_and_new_with_leaf_digest():
