@@ -36,10 +36,27 @@ class Config:
         raise NotImplementedError
 
     def build(self, leaf_param, two_to_one_param, leaves, device):
-        raise NotImplementedError
+        """Generic build (mod.rs:411-523): all leaves in one GPU batch, then one GPU batch per level.  Configs with a
+        fused device-side build (`cpb_merkle_*_build`) override this; the generic form round-trips each level
+        through the host."""
+        leaf_nodes = self.leaf_hash_batch(leaf_param, leaves, device)
+        return leaf_nodes, self.build_from_digests(two_to_one_param, leaf_nodes, device)
+
+    def _pairs(self, nodes):
+        return np.ascontiguousarray(nodes).reshape((-1, 2) + tuple(nodes.shape[1:]))
 
     def build_from_digests(self, two_to_one_param, leaf_digests, device):
-        raise NotImplementedError
+        d = np.ascontiguousarray(leaf_digests, dtype=np.uint64)
+        n = d.shape[0]
+        if n < 2 or n & (n - 1):
+            raise ValueError("`leaves.len() should be power of two and greater than one")
+        nodes = np.empty((n - 1,) + d.shape[1:], dtype=np.uint64)
+        start = n // 2 - 1
+        nodes[start:] = self.two_to_one_batch(two_to_one_param, self._pairs(d), device)
+        while start > 0:
+            upper, start = start, (start - 1) // 2
+            nodes[start:upper] = self.two_to_one_batch(two_to_one_param, self._pairs(nodes[upper:2 * upper + 1]), device)
+        return nodes
 
     def default_leaf_digest(self):
         return np.zeros(self.digest_words, dtype=np.uint64)
@@ -102,17 +119,7 @@ class PedersenByteConfig(Config):
         return leaf_nodes, non_leaf
 
     def build_from_digests(self, two_to_one_param, leaf_digests, device):
-        d = np.ascontiguousarray(leaf_digests, dtype=np.uint64).reshape(-1, 2, 4)
-        n = d.shape[0]
-        if n < 2 or n & (n - 1):
-            raise ValueError("`leaves.len() should be power of two and greater than one")
-        nodes = np.empty((n - 1, 2, 4), dtype=np.uint64)
-        start = n // 2 - 1
-        nodes[start:] = self.two_to_one_batch(two_to_one_param, d.reshape(-1, 2, 2, 4), device)
-        while start > 0:
-            upper, start = start, (start - 1) // 2
-            nodes[start:upper] = self.two_to_one_batch(two_to_one_param, nodes[upper:2 * upper + 1].reshape(-1, 2, 2, 4), device)
-        return nodes
+        return Config.build_from_digests(self, two_to_one_param, np.asarray(leaf_digests, dtype=np.uint64).reshape(-1, 2, 4), device)
 
     def default_leaf_digest(self):
         raise NotImplementedError("Affine::default() (the identity) is not representable as an input digest here")
@@ -144,6 +151,20 @@ class PedersenPoseidonConfig(Config):
 
     def build_from_digests(self, two_to_one_param, leaf_digests, device):
         return PoseidonFieldConfig().build_from_digests(two_to_one_param, leaf_digests, device)
+
+
+class BoweHopwoodByteConfig(Config):
+    """Config{Leaf=[u8], LeafHash=bowe_hopwood::CRH, LeafDigest=InnerDigest=Fq (the x-coordinate),
+    IdentityDigestConverter, TwoToOneHash=bowe_hopwood::TwoToOneCRH} -- the Zcash-style tree (R/crh/bowe_hopwood/mod.rs:
+    112-241).  Hashing runs on the GPU (one batch per level); the level loop is the generic host one."""
+
+    def leaf_hash_batch(self, leaf_param, leaves, device):
+        from .crh import bowe_hopwood as bh
+        return bh.CRH.evaluate_batch(leaf_param, np.ascontiguousarray(leaves, dtype=np.uint8), device)
+
+    def two_to_one_batch(self, param, pairs, device):
+        from .crh import bowe_hopwood as bh
+        return bh.TwoToOneCRH.compress_batch(param, np.asarray(pairs, dtype=np.uint64).reshape(-1, 2, 4), device)
 
 
 # ---- index helpers, mod.rs:728-786

@@ -4,7 +4,7 @@ enters a sponge.  Pure host logic; the permutations run on the GPU (sponge/posei
 
 Python has no integer widths, so the Rust types are spelled out: `UInt(v, bits)`, `SInt(v, bits)`, `usize(v)`;
 a bare `int` is Rust's default `i32`; `bytes` is `&[u8]`/`Vec<u8>`; a uint64 array (..., 4) is native field elements in
-Montgomery limbs (wrap as `Elems(field, limbs)` to make the field explicit); `None`/`Some(x)` is `Option`; `WithLength(x)`
+Montgomery limbs (wrap as `Elems(field, limbs)` to make the field explicit); `Point(curve, xy)` is a twisted-Edwards affine point; `None`/`Some(x)` is `Option`; `WithLength(x)`
 selects the `AbsorbWithLength` form.  The [u8] -> field-element chunking ((MODULUS_BIT_SIZE-1)/8 bytes, little-endian)
 and `Fp::serialize_compressed` (ceil(bits/8) LE bytes) are ark-ff 0.4 conventions.
 """
@@ -39,6 +39,13 @@ class Elems:
     limbs: np.ndarray                        # (k, 4) Montgomery limbs
 
 
+@dataclass(frozen=True, eq=False)
+class Point:
+    """TEAffine<P> (absorb.rs:243-261): curve + (2, 4) affine Montgomery limbs of its base field."""
+    curve: object
+    xy: np.ndarray
+
+
 @dataclass(frozen=True)
 class Some:
     item: object
@@ -67,6 +74,9 @@ def to_sponge_bytes(x) -> bytes:
     if isinstance(x, Elems):
         nb = (x.field.modulus_bit_size + 7) // 8
         return b"".join(v.to_bytes(nb, "little") for v in x.field.to_ints(x.limbs))
+    if isinstance(x, Point):
+        nb = 8 * ((x.curve.base_field.modulus_bit_size + 63) // 64)          # into_bigint().to_bytes_le(): whole limbs
+        return b"".join(v.to_bytes(nb, "little") for v in x.curve.base_field.to_ints(x.xy))
     if isinstance(x, (bytes, bytearray)):
         return bytes(x)
     if isinstance(x, str):
@@ -96,6 +106,10 @@ def _ints(x, field: Field) -> list:
         if x.field.modulus != p:
             raise ValueError("Trying to absorb non-native field elements.")    # field_cast(..).unwrap(), :106-122
         return [np.asarray(x.limbs, dtype=np.uint64).reshape(-1, 4)]
+    if isinstance(x, Point):
+        if x.curve.base_field.modulus != p:
+            raise ValueError("Trying to absorb non-native field elements.")
+        return [np.asarray(x.xy, dtype=np.uint64).reshape(2, 4)]               # [x, y], :258-260
     if isinstance(x, (bytes, bytearray)):
         b = len(x).to_bytes(8, "little") + bytes(x)                            # :137-141
         k = (p.bit_length() - 1) // 8

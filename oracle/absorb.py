@@ -30,6 +30,13 @@ class Fe:            # a prime-field element: canonical value and its modulus
 
 
 @dataclass(frozen=True)
+class TEPoint:       # TEAffine<P> over a prime base field: canonical x, y and the base-field modulus (absorb.rs:243-261)
+    x: int
+    y: int
+    q: int
+
+
+@dataclass(frozen=True)
 class Some:
     item: object
 
@@ -57,6 +64,9 @@ def to_sponge_bytes(x) -> bytes:
         return (x.value % (1 << x.bits)).to_bytes(x.bits // 8, "little")       # :172-174, :191-193 (two's complement)
     if isinstance(x, Fe):
         return x.value.to_bytes((x.p.bit_length() + 7) // 8, "little")         # :155-157
+    if isinstance(x, TEPoint):
+        nb = 8 * ((x.q.bit_length() + 63) // 64)                               # BigInt::to_bytes_le: whole limbs
+        return x.x.to_bytes(nb, "little") + x.y.to_bytes(nb, "little")         # :247-256
     if isinstance(x, (bytes, bytearray)):
         return bytes(x)                                                        # :133-135
     if isinstance(x, str):
@@ -84,6 +94,10 @@ def to_sponge_field_elements(x, p: int) -> list[int]:
         if x.p != p:
             raise ValueError("Trying to absorb non-native field elements.")    # field_cast(..).unwrap(), :106-122
         return [x.value]
+    if isinstance(x, TEPoint):
+        if x.q != p:
+            raise ValueError("Trying to absorb non-native field elements.")
+        return [x.x, x.y]                                                      # :258-260
     if isinstance(x, (bytes, bytearray)):
         return bytes_to_field_elements(len(x).to_bytes(8, "little") + bytes(x), p)   # :137-141
     if isinstance(x, str):

@@ -79,7 +79,34 @@ def test_absorb_encodings_host_side():
     p = f.modulus
     pairs = [([1, -2, 3], [1, -2, 3]), (bytes(range(64)), bytes(range(64))), ("str", "str"), (None, None), (False, False),
              (A.Some(A.usize(5)), OA.Some(OA.UInt(5, 64))), (A.WithLength(b"abc"), OA.WithLength(b"abc")),
-             (A.Elems(f, f.elements([5, p - 1])), [OA.Fe(5, p), OA.Fe(p - 1, p)]), (A.UInt(2**127, 128), OA.UInt(2**127, 128))]
+             (A.Elems(f, f.elements([5, p - 1])), [OA.Fe(5, p), OA.Fe(p - 1, p)]), (A.UInt(2**127, 128), OA.UInt(2**127, 128)),
+             (A.Point(cp.curves.JUBJUB, f.elements([3, 4])), OA.TEPoint(3, 4, p))]
     for g, o in pairs:
         assert A.to_sponge_bytes(g) == OA.to_sponge_bytes(o)
         assert f.to_ints(A.to_sponge_field_elements(g, f)) == OA.to_sponge_field_elements(o, p)
+
+
+def test_generic_config_level_loop_heap_order():
+    """merkle_tree.Config's generic build (used by configs without a fused device build, e.g. Bowe-Hopwood trees) fills the
+    reference's heap-ordered arrays (R/merkle_tree/mod.rs:446-523); checked with a toy hash on the host."""
+    import numpy as np
+    from crypto_primitives_b200.merkle_tree import Config
+
+    class Toy(Config):
+        def leaf_hash_batch(self, prm, leaves, device):
+            return (np.asarray(leaves, dtype=np.uint64) * np.uint64(3) + np.uint64(1)).reshape(-1, 4)
+
+        def two_to_one_batch(self, prm, pairs, device):
+            p = np.asarray(pairs, dtype=np.uint64)
+            return p[:, 0] * np.uint64(5) + p[:, 1] * np.uint64(7) + np.uint64(11)
+
+    n = 16
+    leaves = np.arange(n * 4, dtype=np.uint64).reshape(n, 4)
+    ln, nn = Toy().build(None, None, leaves, 0)
+    assert ln.shape == (n, 4) and nn.shape == (n - 1, 4)
+    full = np.concatenate([nn, ln])
+    for i in range(n - 1):
+        assert np.array_equal(full[i], full[2 * i + 1] * np.uint64(5) + full[2 * i + 2] * np.uint64(7) + np.uint64(11))
+    import pytest
+    with pytest.raises(ValueError):
+        Toy().build_from_digests(None, ln[:6], 0)

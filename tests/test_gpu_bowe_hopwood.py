@@ -75,3 +75,25 @@ def test_setup_generators_and_throughput_shape():
     x[:, 0] = np.arange(1 << 14) & 0xFF
     out = BH.CRH.evaluate_batch(prm, x)
     assert np.array_equal(out[:256], out[256:512]) and len({tuple(r) for r in out[:256]}) == 256
+
+
+def test_merkle_tree_over_bowe_hopwood_digests():
+    """MerkleTree<Config{LeafHash = TwoToOneHash = bowe_hopwood}> through the generic level loop of merkle_tree.Config:
+    arrays against the oracle's tree over the big-integer Bowe-Hopwood restatement; proofs verify, a wrong leaf does not."""
+    from crypto_primitives_b200.merkle_tree import BoweHopwoodByteConfig, MerkleTree
+    from oracle import merkle as OM
+    ow, oprm, oc, prm = setup(63, 9, 4)                  # 63 * 9 * 3 = 1701 bits >= 2 * 256-bit children + 8-byte leaves
+    f = cp.BLS12_381_FR
+    n = 32
+    leaves = np.ascontiguousarray(cref.synth_bytes(77, n * 8).reshape(n, 8))
+    cfg = BoweHopwoodByteConfig()
+    tree = MerkleTree.new(prm, prm, leaves, cfg)
+    comp = lambda l, r: OBH.two_to_one_compress(oprm, ow, l, r)          # noqa: E731
+    otree = OM.MerkleTree.new([bytes(l) for l in leaves], lambda l: OBH.crh_evaluate(oprm, ow, l), comp, comp)
+    assert f.to_ints(tree.leaf_nodes) == otree.leaf_nodes
+    assert f.to_ints(tree.non_leaf_nodes) == otree.non_leaf_nodes
+    root = tree.root()
+    for i in (0, 13, 31):
+        assert tree.generate_proof(i).verify(prm, prm, root, leaves[i], cfg)
+    assert not tree.generate_proof(3).verify(prm, prm, root, leaves[4], cfg)
+    assert tree.generate_multi_proof([1, 2, 30]).verify(prm, prm, root, leaves[[1, 2, 30]], cfg)
