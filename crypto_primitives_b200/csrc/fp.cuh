@@ -25,6 +25,7 @@ namespace cpb {
     }
 
 struct Bls12_381_Fr {
+    static constexpr bool SPLIT_ROUNDS = false;   // Poseidon: partial rounds in a loop of their own (poseidon.cuh)
     static constexpr int P0_POW = 0;          // k > 0: p[0] == 2^32 - 2^k + 1
     static constexpr bool P0_ONE = true;       // p[0] == 1  (then -p^-1 mod 2^32 == -1)
     static constexpr bool P1_ALLONES = true;   // p[1] == 0xffffffff
@@ -36,6 +37,7 @@ struct Bls12_381_Fr {
     CPB_FIELD_TABLE(R2, 0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u)
 };
 struct Bn254_Fr {
+    static constexpr bool SPLIT_ROUNDS = true;   // Poseidon: partial rounds in a loop of their own (poseidon.cuh)
     static constexpr int P0_POW = 0;           // p[0] = 2^32 - 2^28 + 1, but the shift/add form measured slower          // k > 0: p[0] == 2^32 - 2^k + 1
     static constexpr bool P0_ONE = false;       // p[0] == 1  (then -p^-1 mod 2^32 == -1)
     static constexpr bool P1_ALLONES = false;   // p[1] == 0xffffffff
@@ -47,6 +49,7 @@ struct Bn254_Fr {
     CPB_FIELD_TABLE(R2, 0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u)
 };
 struct Jubjub_Fr {
+    static constexpr bool SPLIT_ROUNDS = false;   // Poseidon: partial rounds in a loop of their own (poseidon.cuh)
     static constexpr int P0_POW = 0;          // k > 0: p[0] == 2^32 - 2^k + 1
     static constexpr bool P0_ONE = false;       // p[0] == 1  (then -p^-1 mod 2^32 == -1)
     static constexpr bool P1_ALLONES = false;   // p[1] == 0xffffffff
@@ -58,6 +61,7 @@ struct Jubjub_Fr {
     CPB_FIELD_TABLE(R2, 0x95e57731u, 0x67719aa4u, 0x9ce3fc26u, 0x51b0cef0u, 0xc026e9a5u, 0x69dab7fau, 0x8d127688u, 0x04f6547bu)
 };
 struct Bls12_377_Fr {
+    static constexpr bool SPLIT_ROUNDS = false;   // Poseidon: partial rounds in a loop of their own (poseidon.cuh)
     static constexpr int P0_POW = 0;          // k > 0: p[0] == 2^32 - 2^k + 1
     static constexpr bool P0_ONE = true;       // p[0] == 1  (then -p^-1 mod 2^32 == -1)
     static constexpr bool P1_ALLONES = false;   // p[1] == 0xffffffff
@@ -181,7 +185,7 @@ template <class F, bool WITH_X> CPB_HD void redc_row_impl(u32* E, u32* O, u32* X
         madc_wide_cc(O[4], O[5], pm[5], m);
         madc_wide_cc(O[6], O[7], pm[7], m);
         if (WITH_X) *X = addc(*X, 0);
-        (void)add_cc(e0, 0xffffffffu);                // CF = (e0 != 0): the carry out of E[0] + m
+        (void)add_cc(e0, LIMB_MASK);                  // CF = (e0 != 0): the carry out of E[0] + m
         E[1] = addc_cc(E[1], 0u);
         madc_wide_cc(E[2], E[3], pm[2], m);
         madc_wide_cc(E[4], E[5], pm[4], m);
@@ -191,13 +195,13 @@ template <class F, bool WITH_X> CPB_HD void redc_row_impl(u32* E, u32* O, u32* X
         // adds on the idle ALU pipe instead of an IMAD and an IMAD.HI on the saturated multiply pipe.
         constexpr int K = F::P0_POW > 0 ? F::P0_POW : 1;   // (branch is dead when P0_POW == 0)
         const u32 e0 = E[0];
-        const u32 m = 0u - (e0 + (e0 << K));
+        const u32 m = (0u - (e0 + (e0 << K))) & LIMB_MASK;
         // B = m * (2^k - 1);  m*p[0] = m*2^32 - B;  hi(m*p[0] + e0) = m - B_hi - [B_lo != 0] + [e0 != 0]
-        const u32 b_lo = sub_cc(m << K, m);
-        const u32 b_hi = subc(m >> (32 - K), 0u);
+        const u32 b_lo = sub_cc((m << K) & LIMB_MASK, m);
+        const u32 b_hi = subc(m >> (LIMB_BITS - K), 0u);
         (void)sub_cc(0u, b_lo);                       // CF = (b_lo != 0)
         u32 hw = subc(m, b_hi);
-        (void)add_cc(e0, 0xffffffffu);                // CF = (e0 != 0)
+        (void)add_cc(e0, LIMB_MASK);                  // CF = (e0 != 0)
         hw = addc(hw, 0u);
         mad_wide_cc(O[0], O[1], pm[1], m);
         madc_wide_cc(O[2], O[3], pm[3], m);
@@ -322,8 +326,8 @@ CPB_HD void shift_acc_row_x(u32* E, u32* O, u32& X, const u32* a, u32 bi) {
 
 // limb i (0..8) of p << k
 template <class F> CPB_HD constexpr u32 p_shl(int k, int i) {
-    return (u32)((((i < 8) ? (u64)F::P(i < 8 ? i : 0) : 0ull) << k) |
-                 ((i > 0 && k > 0) ? ((u64)F::P(i - 1) >> (32 - k)) : 0ull));
+    return (u32)(((((i < 8) ? (u64)F::P(i < 8 ? i : 0) : 0ull) << k) |
+                  ((i > 0 && k > 0) ? ((u64)F::P(i - 1) >> (LIMB_BITS - k)) : 0ull)) & LIMB_MASK);
 }
 
 // r (9 limbs) < 2^(K+1) * p  ->  r[0..7] in [0,p)
@@ -466,8 +470,10 @@ template <class F> CPB_HD void fp_sqr(u32* r, const u32* a, const u32* pm) {
 #pragma unroll
         for (int k = 0; k < 6; k++) Oa[k] = addc_cc(Oa[k + 2], 0);
         Oa[6] = addc_cc(0, 0);
-        Oa[7] = addc((i + 8 < 16) ? T[i + 8] : 0u, X);
-        X = 0;
+        // the previous row's overflow word meets the next limb of T here; their sum can carry
+        // (X = 1 is common, T[i + 8] = 0xffffffff is a 2^-32 event -- or an adversarial input)
+        Oa[7] = addc_cc((i + 8 < 16) ? T[i + 8] : 0u, X);
+        X = addc(0, 0);
         detail::redc_row_x<F>(Ea, Oa, X, pm);
     }
     // 8 rows: the last used E = od (low limb zero), O = ev
@@ -520,13 +526,13 @@ template <class F> CPB_HD void fp_inv(u32* r, const u32* x, const u32* pm) {
     e[0] = sub_cc(F::P(0), 2u);
 #pragma unroll
     for (int i = 1; i < 8; i++) e[i] = subc_cc(F::P(i), 0u);
-    // right-to-left binary exponentiation over the 256 bits of p-2
+    // right-to-left binary exponentiation over the 8 limbs of p-2
 #pragma unroll 1
-    for (int k = 0; k < 256; k++) {
+    for (int k = 0; k < 8 * LIMB_BITS; k++) {
         u32 w = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) w = (k >> 5) == i ? e[i] : w;
-        if ((w >> (k & 31)) & 1) fp_mul<F>(acc, acc, base, pm);
+        for (int i = 0; i < 8; i++) w = (k / LIMB_BITS) == i ? e[i] : w;
+        if ((w >> (k % LIMB_BITS)) & 1) fp_mul<F>(acc, acc, base, pm);
         fp_sqr<F>(base, base, pm);
     }
     fp_copy(r, acc);

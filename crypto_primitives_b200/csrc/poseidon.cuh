@@ -60,7 +60,102 @@ template <class F> CPB_HD void pos_sbox(u32* x, u64 alpha, int top_bit, const u3
 // arithmetic body:  [add round constants] -> S-box on T lanes or lane 0 -> linear layer as
 // lazy dot products (T rows of a dense matrix, or the one dense row of the sparse form
 // followed by the rank-one column update).
+// 1: every field uses pos_permute_split; 0: none; unset: per field (F::SPLIT_ROUNDS, measured on the t = 3 kernels:
+// BN254 Fr (57 partial rounds, alpha = 5) gains 3 %, BLS12-381 Fr (31 partial rounds, alpha = 17) loses 1 %).
+#ifdef CPB_POS_SPLIT
+#define CPB_POS_SPLIT_FOR(F) (CPB_POS_SPLIT != 0)
+#else
+#define CPB_POS_SPLIT_FOR(F) (F::SPLIT_ROUNDS)
+#endif
+#ifndef CPB_COL_UNROLL_MAX
+#define CPB_COL_UNROLL_MAX 4
+#endif
+
+// Sparse schedules only: the same permutation with the partial rounds in a loop of their own.  The two
+// halves of the full rounds share one body through a two-trip outer loop, so there is still a single
+// instance of the dense round; the partial-round loop has no full/partial selection and no lane
+// rotation, i.e. none of the register shuffles the merged loop pays at its control-flow joins.
+template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const PoseidonDev& P, const u32* cs, const u32* pm) {
+    const int half = P.rf / 2;
+    int top_bit = 0;
+    for (int i = 63; i > 0; i--)
+        if ((P.alpha >> i) & 1) { top_bit = i; break; }
+    const bool alpha_zero = P.alpha == 0;
+    u32 n[T][8];
+#pragma unroll
+    for (int i = 0; i < T; i++) fp_zero(n[i]);
+#pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {
+#pragma unroll 1
+        for (int q = 0; q < half; q++) {
+            pos_add_vec<F, T>(s, cs + 8 * (P.off_c + (phase * half + q) * T));
+#pragma unroll 1
+            for (int j = 0; j < T; j++) {
+                if (alpha_zero) fp_one<F>(s[0]);
+                else pos_sbox<F>(s[0], P.alpha, top_bit, pm);
+                pos_rotl<T>(s);
+            }
+            const u32* rows = cs + 8 * ((phase == 0 && q == half - 1) ? P.off_mpre : P.off_m);
+#pragma unroll 1
+            for (int i = 0; i < T; i++) {
+                u32 d[8];
+                fp_dot<F, T>(d, s, rows + 8 * T * i, pm);
+#pragma unroll
+                for (int k = 0; k + 1 < T; k++) fp_copy(n[k], n[k + 1]);
+                fp_copy(n[T - 1], d);
+            }
+#pragma unroll
+            for (int i = 0; i < T; i++) fp_copy(s[i], n[i]);
+        }
+        if (phase == 0 && P.rp > 0) {
+            pos_add_vec<F, T>(s, cs + 8 * P.off_cp0);
+            const u32* row = cs + 8 * P.off_sp;
+            const u32* pc = cs + 8 * (P.off_pc + 1);
+#pragma unroll 1
+            for (int k = 0; k < P.rp; k++, row += 8 * (2 * T - 1), pc += 8) {
+                if (alpha_zero) fp_one<F>(s[0]);
+                else pos_sbox<F>(s[0], P.alpha, top_bit, pm);
+                u32 d[8];
+                fp_dot<F, T>(d, s, row, pm);
+                const u32* v = row + 8 * T;
+                if (T <= CPB_COL_UNROLL_MAX) {
+#pragma unroll
+                    for (int j = 1; j < T; j++) {
+                        u32 c[8], tmp[8];
+                        ld_elem(c, v + 8 * (j - 1));
+                        fp_mul<F>(tmp, s[0], c, pm);
+                        fp_add<F>(s[j], s[j], tmp);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int j = 1; j < T; j++) {
+                        u32 c[8], tmp[8];
+                        ld_elem(c, v + 8 * (j - 1));
+                        fp_mul<F>(tmp, s[0], c, pm);
+                        fp_add<F>(s[1], s[1], tmp);
+                        fp_copy(tmp, s[1]);
+#pragma unroll
+                        for (int q = 1; q + 1 < T; q++) fp_copy(s[q], s[q + 1]);
+                        fp_copy(s[T - 1], tmp);
+                    }
+                }
+                if (k + 1 < P.rp) {
+                    u32 c[8];
+                    ld_elem(c, pc);
+                    fp_add<F>(s[0], d, c);
+                } else {
+                    fp_copy(s[0], d);
+                }
+            }
+        }
+    }
+}
+
 template <class F, int T> CPB_HD void pos_permute(u32 (&s)[T][8], const PoseidonDev& P, const u32* cs, const u32* pm) {
+    if (CPB_POS_SPLIT_FOR(F) && P.sparse) {
+        pos_permute_split<F, T>(s, P, cs, pm);
+        return;
+    }
     const int half = P.rf / 2, total = P.rf + P.rp;
     int top_bit = 0;
     for (int i = 63; i > 0; i--)
@@ -113,9 +208,6 @@ template <class F, int T> CPB_HD void pos_permute(u32 (&s)[T][8], const Poseidon
         } else {
             // s_j += v_j * s_0 for j >= 1 (old s_0), then s_0 <- row product d (+ next lane-0 constant)
             const u32* v = rows + 8 * T;
-#ifndef CPB_COL_UNROLL_MAX
-#define CPB_COL_UNROLL_MAX 4
-#endif
             if (T <= CPB_COL_UNROLL_MAX) {
 #pragma unroll
                 for (int j = 1; j < T; j++) {

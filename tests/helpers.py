@@ -70,14 +70,48 @@ def synth_elems(seed, shape_elems, p):
     return cref.synth_field_mont(seed, n, p).reshape(*shape_elems, 4)
 
 
-def build_host_shim(name):
+def build_host_shim(name, defines=(), tag=""):
     """g++ build of tests/host/<name>.cpp (device code with PTX primitives emulated) -> CDLL."""
     src = os.path.join(ROOT, "tests", "host", name + ".cpp")
     out_dir = os.path.join(ROOT, "tests", "host", "_build")
     os.makedirs(out_dir, exist_ok=True)
-    so = os.path.join(out_dir, name + ".so")
+    so = os.path.join(out_dir, name + tag + ".so")
     deps = [src] + [os.path.join(ROOT, "crypto_primitives_b200", "csrc", f)
                     for f in os.listdir(os.path.join(ROOT, "crypto_primitives_b200", "csrc")) if f.endswith(("cuh", "hpp"))]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", src, "-o", so])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", *[f"-D{d}" for d in defines], "-x", "c++", src, "-o", so])
     return C.CDLL(so)
+
+
+def crafted_sbox_inputs(cfg, count, seed=1):
+    """CRH inputs (count, 2, 4) in Montgomery limbs whose first-round S-box operand on lane `capacity` is a value whose
+    512-bit square has all-ones limbs in its upper half -- the operands on which a reduction that drops a rare carry
+    gives a wrong digest (tests/test_fp_host.py has the field-level versions).  The kernel squares the Montgomery
+    representation s = in0 + ark[0][capacity] (both Montgomery), so in0 = s_crafted - ark."""
+    import math
+    import random
+    rnd = random.Random(seed)
+    p = cfg.p
+    top_bits = (p * p).bit_length()
+    ark_m = (cfg.ark[0][cfg.capacity] << 256) % p
+    rows = []
+    while len(rows) < count:
+        run = rnd.choice((1, 1, 2))
+        k = rnd.randrange(8, 15 - run + 1)
+        if 32 * (k + run) >= top_bits - 2:
+            continue
+        v = rnd.randrange(1, (p * p) >> (32 * (k + run))) << (32 * (k + run))
+        for j in range(run):
+            v |= 0xFFFFFFFF << (32 * (k + j))
+        v |= (0x80000000 | rnd.getrandbits(31)) << (32 * (k - 1))
+        v |= rnd.getrandbits(32 * (k - 1))
+        s = math.isqrt(v)
+        if s >= p:
+            continue
+        in0 = (s - ark_m) % p                         # Montgomery limbs of the first input element
+        rows.append([in0, rnd.randrange(p)])
+    out = np.zeros((count, 2, 4), dtype=np.uint64)
+    for i, (a, b) in enumerate(rows):
+        for j, v in enumerate((a, b)):
+            out[i, j] = [(v >> (64 * w)) & 0xFFFFFFFFFFFFFFFF for w in range(4)]
+    return out

@@ -123,6 +123,24 @@ def test_full_size_tree_properties():
     assert np.array_equal(t2.non_leaf_nodes, nodes)
 
 
+@pytest.mark.parametrize("which,logn", [("bls_default_r2", 20), ("bn254_r2", 22), ("bn254_r2", 24)])
+def test_full_size_trees_equal_the_oracle_node_for_node(which, logn):
+    """BASELINE configs 2 and 4 at full size: every leaf digest and every inner node against the C oracle run on all host
+    threads (about 7 s / 30 s / 2 min of CPU).  A defect that hits one hash in 10^8 -- which sampled checks cannot see --
+    changes the root here."""
+    import os
+    _, ocfg = oracle_config(which)
+    cfg = product_config(which)
+    n = 1 << logn
+    leaves = synth_elems(40 + logn, (n, 2), ocfg.p)
+    t = MerkleTree.new(cfg, cfg, leaves)
+    O = cref.Poseidon(ocfg)
+    ln, nn = cref.poseidon_merkle(O, O, leaves, threads=os.cpu_count() or 8)
+    assert np.array_equal(t.non_leaf_nodes[0], nn[0]), "root differs"
+    assert np.array_equal(t.leaf_nodes, ln)
+    assert np.array_equal(t.non_leaf_nodes, nn)
+
+
 def test_batched_path_verification():
     """All 4096 paths of a tree verified in one launch; tampered leaf / sibling / index / root are rejected."""
     _, ocfg = oracle_config("bls_default_r2")
