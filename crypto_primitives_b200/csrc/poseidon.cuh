@@ -152,9 +152,11 @@ template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const Po
 }
 
 template <class F, int T> CPB_HD void pos_permute(u32 (&s)[T][8], const PoseidonDev& P, const u32* cs, const u32* pm) {
-    if (CPB_POS_SPLIT_FOR(F) && P.sparse) {
-        pos_permute_split<F, T>(s, P, cs, pm);
-        return;
+    if constexpr (CPB_POS_SPLIT_FOR(F)) {
+        if (P.sparse) {
+            pos_permute_split<F, T>(s, P, cs, pm);
+            return;
+        }
     }
     const int half = P.rf / 2, total = P.rf + P.rp;
     int top_bit = 0;
