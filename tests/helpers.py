@@ -83,7 +83,7 @@ def build_host_shim(name, defines=(), tag=""):
     return C.CDLL(so)
 
 
-def crafted_sbox_inputs(cfg, count, seed=1):
+def crafted_sbox_inputs(cfg, count, seed=1, limb64=False):
     """CRH inputs (count, 2, 4) in Montgomery limbs whose first-round S-box operand on lane `capacity` is a value whose
     512-bit square has all-ones limbs in its upper half -- the operands on which a reduction that drops a rare carry
     gives a wrong digest (tests/test_fp_host.py has the field-level versions).  The kernel squares the Montgomery
@@ -98,6 +98,8 @@ def crafted_sbox_inputs(cfg, count, seed=1):
     while len(rows) < count:
         run = rnd.choice((1, 1, 2))
         k = rnd.randrange(8, 15 - run + 1)
+        if limb64:                                    # all-ones 64-bit limbs (the C oracle works on 4 x 64)
+            run, k = 2, rnd.choice((8, 10, 12))
         if 32 * (k + run) >= top_bits - 2:
             continue
         v = rnd.randrange(1, (p * p) >> (32 * (k + run))) << (32 * (k + run))

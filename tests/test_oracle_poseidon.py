@@ -69,6 +69,19 @@ def test_c_restatement_equals_python(which, L):
     assert got == [OP.crh_evaluate(cfg, ints[i * L:(i + 1) * L]) for i in range(n)]
 
 
+@pytest.mark.parametrize("which", ["bls_default_r2", "bn254_r2"])
+def test_c_restatement_on_crafted_carry_operands(which):
+    """The C oracle against the big-integer oracle on inputs whose first S-box operand squares to all-ones limbs
+    (32- and 64-bit aligned): the checker itself must not have a rare-carry defect."""
+    from helpers import crafted_sbox_inputs
+    _, cfg = oracle_config(which)
+    for limb64 in (False, True):
+        x = crafted_sbox_inputs(cfg, 40, seed=3, limb64=limb64)
+        ints = cref.mont_to_ints(x, cfg.p)
+        got = cref.mont_to_ints(cref.Poseidon(cfg).crh_batch(x, threads=2), cfg.p)
+        assert got == [OP.crh_evaluate(cfg, ints[2 * i:2 * i + 2]) for i in range(40)]
+
+
 def test_c_merkle_equals_python_heap_order():
     _, cfg = oracle_config("jubjub_merkle_fixture")
     n, L = 32, 3                                                  # R/merkle_tree/tests/mod.rs:293-296 shape
