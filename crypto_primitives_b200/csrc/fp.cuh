@@ -293,6 +293,58 @@ namespace detail {
 
 template <class F> CPB_HD void redc_row_x(u32* E, u32* O, u32& X, const u32* pm) { redc_row_impl<F, true>(E, O, &X, pm); }
 
+// Reduction row of the squaring: V <- V/2^32 + tin*2^256, then V += m*p as in redc_row_impl.
+// On entry O is the previous row's even accumulator (low limb zero after its reduction), E the previous odd one,
+// X the previous overflow word (it sat at 2^288, now at 2^256) and tin the limb of the square that enters the
+// window at 2^256.  The two-limb shift of the old even accumulator is folded into the addend operand of the odd
+// chain's multiply-adds (as next_row does for a product row), so it costs no instructions.
+// tin + X may carry (X = 1 is common, tin = 0xffffffff a 2^-32 event): both are added with carry-out into the new X.
+#ifndef CPB_SQR_FOLD
+#define CPB_SQR_FOLD 1
+#endif
+template <class F> CPB_HD void redc_row_shift_x(u32* E, u32* O, u32& X, u32 tin, const u32* pm) {
+    E[0] = add_cc(E[0], O[1]);
+    u32 xn;
+    if (F::P0_ONE) {
+        const u32 c0 = addc(0u, 0u);                  // carry into 2^32; joins the even chain below
+        const u32 e0 = E[0];
+        const u32 m = sub_cc(0u, e0);                 // CF = (e0 != 0)
+        if (F::P1_ALLONES) {
+            const u32 hi1 = subc(m, 0u);              // m - [m != 0]
+            O[0] = add_cc(O[2], e0);
+            O[1] = addc_cc(O[3], hi1);
+        } else {
+            mad_wide_cc_from(O[0], O[1], pm[1], m, O[2], O[3]);
+        }
+        madc_wide_cc_from(O[2], O[3], pm[3], m, O[4], O[5]);
+        madc_wide_cc_from(O[4], O[5], pm[5], m, O[6], O[7]);
+        madc_wide_cc_from(O[6], O[7], pm[7], m, 0u, tin);
+        xn = addc(0u, 0u);
+        O[7] = add_cc(O[7], X);
+        xn = addc(xn, 0u);
+        (void)add_cc(e0, LIMB_MASK);                  // CF = (e0 != 0): the carry out of E[0] + m
+        E[1] = addc_cc(E[1], c0);
+        madc_wide_cc(E[2], E[3], pm[2], m);
+        madc_wide_cc(E[4], E[5], pm[4], m);
+        madc_wide_cc(E[6], E[7], pm[6], m);
+    } else {
+        const u32 m = mul_lo(E[0], F::NINV);          // (does not touch the carry flag)
+        madc_wide_cc_from(O[0], O[1], pm[1], m, O[2], O[3]);
+        madc_wide_cc_from(O[2], O[3], pm[3], m, O[4], O[5]);
+        madc_wide_cc_from(O[4], O[5], pm[5], m, O[6], O[7]);
+        madc_wide_cc_from(O[6], O[7], pm[7], m, 0u, tin);
+        xn = addc(0u, 0u);
+        O[7] = add_cc(O[7], X);
+        xn = addc(xn, 0u);
+        mad_wide_cc(E[0], E[1], pm[0], m);
+        madc_wide_cc(E[2], E[3], pm[2], m);
+        madc_wide_cc(E[4], E[5], pm[4], m);
+        madc_wide_cc(E[6], E[7], pm[6], m);
+    }
+    O[7] = addc_cc(O[7], 0u);
+    X = addc(xn, 0u);
+}
+
 // V += a * bi   (no shift)
 CPB_HD void acc_row_x(u32* E, u32* O, u32& X, const u32* a, u32 bi) {
     mad_wide_cc(O[0], O[1], a[1], bi);
@@ -466,6 +518,10 @@ template <class F> CPB_HD void fp_sqr(u32* r, const u32* a, const u32* pm) {
         // shift the window by one limb: roles of ev/od swap each row
         u32* Ea = (i & 1) ? od : ev;    // new even accumulator (previous odd)
         u32* Oa = (i & 1) ? ev : od;    // previous even accumulator: low limb is zero, limb 1 moves into Ea[0]
+#if CPB_SQR_FOLD
+        detail::redc_row_shift_x<F>(Ea, Oa, X, T[(i + 8) & 15], pm);
+        continue;
+#endif
         Ea[0] = add_cc(Ea[0], Oa[1]);
 #pragma unroll
         for (int k = 0; k < 6; k++) Oa[k] = addc_cc(Oa[k + 2], 0);

@@ -57,6 +57,11 @@ CPB_D void madc_wide_cc_from(u32& lo, u32& hi, u32 a, u32 b, u32 c_lo, u32 c_hi)
     asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;"
                  : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b), "r"(c_lo), "r"(c_hi));
 }
+// (lo,hi) = a*b + (c_lo,c_hi), starting a chain.
+CPB_D void mad_wide_cc_from(u32& lo, u32& hi, u32 a, u32 b, u32 c_lo, u32 c_hi) {
+    asm volatile("mad.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;"
+                 : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b), "r"(c_lo), "r"(c_hi));
+}
 // (lo,hi) = a*b + CF; ends a chain (cannot overflow: a*b + 1 < 2^64).
 CPB_D void madc_wide_end(u32& lo, u32& hi, u32 a, u32 b) {
     asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b));
@@ -100,6 +105,10 @@ inline void madc_wide_cc(u32& lo, u32& hi, u32 a, u32 b) {
 }
 inline void madc_wide_cc_from(u32& lo, u32& hi, u32 a, u32 b, u32 c_lo, u32 c_hi) {
     unsigned __int128 s = (unsigned __int128)detail::join(c_lo, c_hi) + (u64)a * b + detail::cf();
+    detail::split(s, lo, hi); detail::cf() = (u32)(s >> (2 * detail::W));
+}
+inline void mad_wide_cc_from(u32& lo, u32& hi, u32 a, u32 b, u32 c_lo, u32 c_hi) {
+    unsigned __int128 s = (unsigned __int128)detail::join(c_lo, c_hi) + (u64)a * b;
     detail::split(s, lo, hi); detail::cf() = (u32)(s >> (2 * detail::W));
 }
 inline void madc_wide_end(u32& lo, u32& hi, u32 a, u32 b) {
