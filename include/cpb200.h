@@ -12,6 +12,10 @@
  * (`BigInt<4>` in `.0.0`), so a `&[Fr]` can be passed without conversion.  A curve point is
  * affine (x, y): 8 x uint64_t.  Byte inputs are plain uint8_t.  All arrays are dense, C order.
  *
+ * PRECONDITION.  Field elements and point coordinates passed in must be fully reduced (< p), as ark-ff guarantees for
+ * every `Fp` value; this is not checked on the hot path.  Unreduced limbs yield unspecified digests -- never a memory
+ * error (no address is derived from a field value).  cpb_field_to_montgomery() does check its canonical inputs.
+ *
  * POINTERS.  Functions without suffix take HOST pointers and perform the H2D/D2H copies
  * themselves on the context's stream; `_dev` functions take DEVICE pointers (on the context's
  * device) plus a CUDA stream handle (`cudaStream_t` passed as void*, NULL = default stream),
