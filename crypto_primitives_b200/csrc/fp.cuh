@@ -25,7 +25,7 @@ namespace cpb {
     }
 
 struct Bls12_381_Fr {
-    static constexpr bool SPLIT_ROUNDS = false;   // Poseidon: partial rounds in a loop of their own (poseidon.cuh)
+    static constexpr bool SPLIT_ROUNDS = true;   // Poseidon: partial rounds in a loop of their own (poseidon.cuh)
     static constexpr int P0_POW = 0;          // k > 0: p[0] == 2^32 - 2^k + 1
     static constexpr bool P0_ONE = true;       // p[0] == 1  (then -p^-1 mod 2^32 == -1)
     static constexpr bool P1_ALLONES = true;   // p[1] == 0xffffffff
@@ -49,7 +49,7 @@ struct Bn254_Fr {
     CPB_FIELD_TABLE(R2, 0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u)
 };
 struct Jubjub_Fr {
-    static constexpr bool SPLIT_ROUNDS = false;   // Poseidon: partial rounds in a loop of their own (poseidon.cuh)
+    static constexpr bool SPLIT_ROUNDS = true;   // Poseidon: partial rounds in a loop of their own (poseidon.cuh)
     static constexpr int P0_POW = 0;          // k > 0: p[0] == 2^32 - 2^k + 1
     static constexpr bool P0_ONE = false;       // p[0] == 1  (then -p^-1 mod 2^32 == -1)
     static constexpr bool P1_ALLONES = false;   // p[1] == 0xffffffff
@@ -61,7 +61,7 @@ struct Jubjub_Fr {
     CPB_FIELD_TABLE(R2, 0x95e57731u, 0x67719aa4u, 0x9ce3fc26u, 0x51b0cef0u, 0xc026e9a5u, 0x69dab7fau, 0x8d127688u, 0x04f6547bu)
 };
 struct Bls12_377_Fr {
-    static constexpr bool SPLIT_ROUNDS = false;   // Poseidon: partial rounds in a loop of their own (poseidon.cuh)
+    static constexpr bool SPLIT_ROUNDS = true;   // Poseidon: partial rounds in a loop of their own (poseidon.cuh)
     static constexpr int P0_POW = 0;          // k > 0: p[0] == 2^32 - 2^k + 1
     static constexpr bool P0_ONE = true;       // p[0] == 1  (then -p^-1 mod 2^32 == -1)
     static constexpr bool P1_ALLONES = false;   // p[1] == 0xffffffff

@@ -60,12 +60,16 @@ template <class F> CPB_HD void pos_sbox(u32* x, u64 alpha, int top_bit, const u3
 // arithmetic body:  [add round constants] -> S-box on T lanes or lane 0 -> linear layer as
 // lazy dot products (T rows of a dense matrix, or the one dense row of the sparse form
 // followed by the rank-one column update).
-// 1: every field uses pos_permute_split; 0: none; unset: per field (F::SPLIT_ROUNDS, measured on the t = 3 kernels:
-// BN254 Fr (57 partial rounds, alpha = 5) gains 3 %, BLS12-381 Fr (31 partial rounds, alpha = 17) loses 1 %).
+// 1: every field uses pos_permute_split; 0: none; unset: per field (F::SPLIT_ROUNDS).  Measured on the t = 3 kernels:
+// BN254 Fr (57 partial rounds, alpha = 5) +3 %; BLS12-381 Fr (31 partial rounds, alpha = 17) -1 % before and +0.9 %
+// after the squaring lost 51 instructions -- so every field uses the split form now.
 #ifdef CPB_POS_SPLIT
 #define CPB_POS_SPLIT_FOR(F) (CPB_POS_SPLIT != 0)
 #else
 #define CPB_POS_SPLIT_FOR(F) (F::SPLIT_ROUNDS)
+#endif
+#ifndef CPB_SBOX5
+#define CPB_SBOX5 1        // straight-line x^5 in the partial-round loop (+0.6 % on BN254 Fr; other exponents use the bit loop)
 #endif
 #ifndef CPB_COL_UNROLL_MAX
 #define CPB_COL_UNROLL_MAX 4
@@ -113,6 +117,14 @@ template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const Po
             const u32* pc = cs + 8 * (P.off_pc + 1);
 #pragma unroll 1
             for (int k = 0; k < P.rp; k++, row += 8 * (2 * T - 1), pc += 8) {
+#if CPB_SBOX5
+                if (P.alpha == 5) {                   // straight-line x^5
+                    u32 x2[8];
+                    fp_sqr<F>(x2, s[0], pm);
+                    fp_sqr<F>(x2, x2, pm);
+                    fp_mul<F>(s[0], x2, s[0], pm);
+                } else
+#endif
                 if (alpha_zero) fp_one<F>(s[0]);
                 else pos_sbox<F>(s[0], P.alpha, top_bit, pm);
                 u32 d[8];
