@@ -1,4 +1,4 @@
-"""Short workload for ncu captures.  usage: ncu_target.py [bls|bn254] [compress|merkle|pedersen]"""
+"""Short workload for ncu captures.  usage: ncu_target.py [bls|bn254] [compress|merkle|pedersen|pedersen8]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -18,7 +18,7 @@ else:
 dev = torch.device("cuda:0")
 n = 1 << logn
 st = torch.cuda.current_stream().cuda_stream
-if what == "pedersen":
+if what in ("pedersen", "pedersen8"):
     from crypto_primitives_b200.commitment.pedersen import Commitment
     from crypto_primitives_b200.crh.pedersen import Window
 
@@ -26,6 +26,8 @@ if what == "pedersen":
         def __init__(self, seed): self.g = np.random.default_rng(seed)
         def field(self, q): return int.from_bytes(self.g.bytes(40), "little") % q
     prm = Commitment.setup(Rng(1), Window(4, 256))
+    if what == "pedersen8":
+        prm.chunk_bits = 8                      # the shared-memory / TMA double-buffered kernel
     ctx = prm.context(0)
     inp = torch.randint(0, 256, (n, 128), dtype=torch.uint8, device=dev)
     out = torch.empty((n, 2, 4), dtype=torch.int64, device=dev)
