@@ -14,7 +14,7 @@ u64p = C.POINTER(C.c_uint64)
 u8p = C.POINTER(C.c_uint8)
 vp = C.c_void_p
 
-CPB_OK, CPB_BAD_LENGTH, CPB_BAD_PARAMS, CPB_NOT_POW2, CPB_CUDA_ERROR, CPB_NO_DEVICE, CPB_UNSUPPORTED, CPB_NULL_POINTER = range(8)
+CPB_OK, CPB_BAD_LENGTH, CPB_BAD_PARAMS, CPB_NOT_POW2, CPB_CUDA_ERROR, CPB_NO_DEVICE, CPB_UNSUPPORTED, CPB_NULL_POINTER, CPB_INTERNAL_ERROR = range(9)
 
 # name -> (restype, argtypes); mirrors include/cpb200.h one to one (tests/test_abi.py checks it).
 SIGNATURES = {

@@ -1,6 +1,8 @@
 // common.cuh -- host-side plumbing shared by the C-ABI translation units: error reporting,
 // CUDA call checking, device buffers, TMA (cp.async.bulk) staging helper for kernels.
 #pragma once
+#include <exception>
+#include <new>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -15,6 +17,20 @@ namespace cpb {
 
 std::string& last_error_ref();
 cpb_status fail(cpb_status st, const char* fmt, ...);
+
+// Every extern "C" entry point runs its body through this: no C++ exception (std::bad_alloc from a host vector,
+// std::system_error from a mutex) crosses the C ABI.
+template <class Fn> cpb_status guarded(Fn&& fn) noexcept {
+    try {
+        return fn();
+    } catch (const std::bad_alloc&) {
+        return fail(CPB_INTERNAL_ERROR, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(CPB_INTERNAL_ERROR, "unexpected exception: %s", e.what());
+    } catch (...) {
+        return fail(CPB_INTERNAL_ERROR, "unexpected exception");
+    }
+}
 
 #define CPB_CUDA(call)                                                                           \
     do {                                                                                         \

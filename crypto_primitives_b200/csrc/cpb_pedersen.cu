@@ -590,12 +590,15 @@ extern "C" {
 
 cpb_status cpb_pedersen_ctx_create(int curve_id, int window_size, int num_windows, const uint64_t* generators_xy,
                                    size_t n_rand, const uint64_t* rand_generators_xy, int device, cpb_pedersen_ctx** out) {
+    return cpb::guarded([&]() -> cpb_status {
     return cpb_pedersen_ctx_create_ex(curve_id, window_size, num_windows, generators_xy, n_rand, rand_generators_xy, device, 0, out);
+    });
 }
 
 cpb_status cpb_pedersen_ctx_create_ex(int curve_id, int window_size, int num_windows, const uint64_t* generators_xy,
                                       size_t n_rand, const uint64_t* rand_generators_xy, int device, int chunk_bits,
                                       cpb_pedersen_ctx** out) {
+    return cpb::guarded([&]() -> cpb_status {
     if (!out) return fail(CPB_NULL_POINTER, "null out");
     if (chunk_bits == 0) {
         // default: the widest lookup whose tables stay under 1 GiB (16 bits: 0.5 GB for a 1024-bit input + 252
@@ -688,6 +691,7 @@ cpb_status cpb_pedersen_ctx_create_ex(int curve_id, int window_size, int num_win
     }
     *out = c;
     return CPB_OK;
+    });
 }
 
 void cpb_pedersen_ctx_destroy(cpb_pedersen_ctx* c) {
@@ -703,37 +707,46 @@ void cpb_pedersen_ctx_destroy(cpb_pedersen_ctx* c) {
 // ---- device-pointer entry points
 cpb_status cpb_pedersen_crh_batch_dev(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, size_t stride, uint64_t* out_xy,
                                       size_t n, void* stream) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(ped_check(c));
     CPB_TRY(check_len(c, len, false));
     DeviceGuard g(c->device);
     return launch_hash(c, in, len, stride, nullptr, (u32*)out_xy, n, 0, (cudaStream_t)stream);
+    });
 }
 cpb_status cpb_pedersen_crh_x_batch_dev(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, size_t stride, uint64_t* out_x,
                                         size_t n, void* stream) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(ped_check(c));
     CPB_TRY(check_len(c, len, false));
     DeviceGuard g(c->device);
     return launch_hash(c, in, len, stride, nullptr, (u32*)out_x, n, 1, (cudaStream_t)stream);
+    });
 }
 cpb_status cpb_pedersen_commit_batch_dev(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, size_t stride,
                                          const uint8_t* randomness_le32, uint64_t* out_xy, size_t n, void* stream) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(ped_check(c));
     if (c->n_rand == 0) return fail(CPB_BAD_PARAMS, "context has no randomness generators");
     if (!randomness_le32 && n) return fail(CPB_NULL_POINTER, "null randomness");
     CPB_TRY(check_len(c, len, true));
     DeviceGuard g(c->device);
     return launch_hash(c, in, len, stride, randomness_le32, (u32*)out_xy, n, 0, (cudaStream_t)stream);
+    });
 }
 cpb_status cpb_pedersen_two_to_one_batch_dev(cpb_pedersen_ctx* c, const uint64_t* children_xy, uint64_t* out_xy, size_t n,
                                              void* scratch_128n, void* stream) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(ped_check(c));
     if (n && !scratch_128n) return fail(CPB_NULL_POINTER, "null scratch");
     DeviceGuard g(c->device);
     return two_to_one_dev(c, (const u32*)children_xy, (u32*)out_xy, n, (u32*)scratch_128n, (cudaStream_t)stream);
+    });
 }
 cpb_status cpb_merkle_pedersen_build_dev(cpb_pedersen_ctx* leaf, cpb_pedersen_ctx* node, const uint8_t* leaves,
                                          size_t leaf_len, size_t leaf_stride, size_t n, uint64_t* leaf_nodes_xy,
                                          uint64_t* non_leaf_nodes_xy, void* scratch_64n, void* stream) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(ped_check(leaf));
     CPB_TRY(ped_check(node));
     if (leaf->device != node->device || leaf->field_id != node->field_id)
@@ -745,10 +758,12 @@ cpb_status cpb_merkle_pedersen_build_dev(cpb_pedersen_ctx* leaf, cpb_pedersen_ct
     cudaStream_t st = (cudaStream_t)stream;
     CPB_TRY(launch_hash(leaf, leaves, leaf_len, leaf_stride, nullptr, (u32*)leaf_nodes_xy, n, 0, st));
     return pedersen_levels(node, (const u32*)leaf_nodes_xy, n, (u32*)non_leaf_nodes_xy, (u32*)scratch_64n, st);
+    });
 }
 cpb_status cpb_merkle_mixed_build_dev(cpb_pedersen_ctx* leaf, cpb_poseidon_ctx* node, const uint8_t* leaves, size_t leaf_len,
                                       size_t leaf_stride, size_t n, uint64_t* leaf_nodes, uint64_t* non_leaf_nodes,
                                       void* stream) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(ped_check(leaf));
     if (!node) return fail(CPB_NULL_POINTER, "null context");
     if (cpb_poseidon_ctx_field(node) != leaf->field_id || cpb_poseidon_ctx_device(node) != leaf->device)
@@ -759,6 +774,7 @@ cpb_status cpb_merkle_mixed_build_dev(cpb_pedersen_ctx* leaf, cpb_poseidon_ctx* 
     cudaStream_t st = (cudaStream_t)stream;
     CPB_TRY(launch_hash(leaf, leaves, leaf_len, leaf_stride, nullptr, (u32*)leaf_nodes, n, 1, st));
     return cpb_merkle_poseidon_from_digests_dev(node, leaf_nodes, n, non_leaf_nodes, stream);
+    });
 }
 
 // ---- host-pointer entry points
@@ -787,19 +803,26 @@ static cpb_status ped_host_hash(cpb_pedersen_ctx* c, const uint8_t* in, size_t l
     return CPB_OK;
 }
 cpb_status cpb_pedersen_crh_batch(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, size_t stride, uint64_t* out_xy, size_t n) {
+    return cpb::guarded([&]() -> cpb_status {
     return ped_host_hash(c, in, len, stride, nullptr, out_xy, n, 0, false);
+    });
 }
 cpb_status cpb_pedersen_crh_x_batch(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, size_t stride, uint64_t* out_x, size_t n) {
+    return cpb::guarded([&]() -> cpb_status {
     return ped_host_hash(c, in, len, stride, nullptr, out_x, n, 1, false);
+    });
 }
 cpb_status cpb_pedersen_commit_batch(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, size_t stride,
                                      const uint8_t* randomness_le32, uint64_t* out_xy, size_t n) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(ped_check(c));
     if (c->n_rand == 0) return fail(CPB_BAD_PARAMS, "context has no randomness generators");
     if (!randomness_le32 && n) return fail(CPB_NULL_POINTER, "null randomness");
     return ped_host_hash(c, in, len, stride, randomness_le32, out_xy, n, 0, true);
+    });
 }
 cpb_status cpb_pedersen_two_to_one_batch(cpb_pedersen_ctx* c, const uint64_t* children_xy, uint64_t* out_xy, size_t n) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(ped_check(c));
     if (n == 0) return CPB_OK;
     if (!children_xy || !out_xy) return fail(CPB_NULL_POINTER, "null buffer");
@@ -813,9 +836,11 @@ cpb_status cpb_pedersen_two_to_one_batch(cpb_pedersen_ctx* c, const uint64_t* ch
     CPB_CUDA(cudaMemcpyAsync(out_xy, c->s_out.ptr, n * 64, cudaMemcpyDeviceToHost, c->stream));
     CPB_CUDA(cudaStreamSynchronize(c->stream));
     return CPB_OK;
+    });
 }
 cpb_status cpb_merkle_pedersen_build(cpb_pedersen_ctx* leaf, cpb_pedersen_ctx* node, const uint8_t* leaves, size_t leaf_len,
                                      size_t n, uint64_t* leaf_nodes_xy, uint64_t* non_leaf_nodes_xy) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(ped_check(leaf));
     CPB_TRY(ped_check(node));
     if (!pow2_gt1(n)) return fail(CPB_NOT_POW2, "leaves.len() should be power of two and greater than one (got %zu)", n);
@@ -835,9 +860,11 @@ cpb_status cpb_merkle_pedersen_build(cpb_pedersen_ctx* leaf, cpb_pedersen_ctx* n
     CPB_CUDA(cudaMemcpyAsync(non_leaf_nodes_xy, d_nodes, (n - 1) * 64, cudaMemcpyDeviceToHost, st));
     CPB_CUDA(cudaStreamSynchronize(st));
     return CPB_OK;
+    });
 }
 cpb_status cpb_merkle_mixed_build(cpb_pedersen_ctx* leaf, cpb_poseidon_ctx* node, const uint8_t* leaves, size_t leaf_len,
                                   size_t n, uint64_t* leaf_nodes, uint64_t* non_leaf_nodes) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(ped_check(leaf));
     if (!node) return fail(CPB_NULL_POINTER, "null context");
     if (!pow2_gt1(n)) return fail(CPB_NOT_POW2, "leaves.len() should be power of two and greater than one (got %zu)", n);
@@ -856,6 +883,7 @@ cpb_status cpb_merkle_mixed_build(cpb_pedersen_ctx* leaf, cpb_poseidon_ctx* node
     CPB_CUDA(cudaMemcpyAsync(non_leaf_nodes, d_nodes, (n - 1) * 32, cudaMemcpyDeviceToHost, st));
     CPB_CUDA(cudaStreamSynchronize(st));
     return CPB_OK;
+    });
 }
 
 }  // extern "C"
@@ -927,6 +955,7 @@ extern "C" {
 
 cpb_status cpb_bowe_hopwood_ctx_create(int curve_id, int window_size, int num_windows, const uint64_t* generators_xy, int device,
                                        cpb_bowe_hopwood_ctx** out) {
+    return cpb::guarded([&]() -> cpb_status {
     if (!out) return fail(CPB_NULL_POINTER, "null out");
     *out = nullptr;
     CurveInfo ci;
@@ -994,6 +1023,7 @@ cpb_status cpb_bowe_hopwood_ctx_create(int curve_id, int window_size, int num_wi
     }
     *out = c;
     return CPB_OK;
+    });
 }
 
 void cpb_bowe_hopwood_ctx_destroy(cpb_bowe_hopwood_ctx* c) {
@@ -1009,20 +1039,25 @@ void cpb_bowe_hopwood_ctx_destroy(cpb_bowe_hopwood_ctx* c) {
 
 cpb_status cpb_bowe_hopwood_crh_batch_dev(cpb_bowe_hopwood_ctx* c, const uint8_t* in, size_t len, size_t stride, uint64_t* out_x,
                                           size_t n, void* stream) {
+    return cpb::guarded([&]() -> cpb_status {
     if (!c) return fail(CPB_NULL_POINTER, "null context");
     DeviceGuard g(c->device);
     return bh_launch(c, in, len, stride, (u32*)out_x, n, (cudaStream_t)stream);
+    });
 }
 cpb_status cpb_bowe_hopwood_two_to_one_batch_dev(cpb_bowe_hopwood_ctx* c, const uint64_t* children_x, uint64_t* out_x, size_t n,
                                                  void* scratch, void* stream) {
+    return cpb::guarded([&]() -> cpb_status {
     if (!c) return fail(CPB_NULL_POINTER, "null context");
     if (n && !scratch) return fail(CPB_NULL_POINTER, "null scratch");
     DeviceGuard g(c->device);
     return bh_two_to_one_dev(c, (const u32*)children_x, (u32*)out_x, n, (uint8_t*)scratch, (cudaStream_t)stream);
+    });
 }
 size_t cpb_bowe_hopwood_two_to_one_scratch_bytes(const cpb_bowe_hopwood_ctx* c, size_t n) { return c ? n * bh_two_to_one_stride(c) : 0; }
 
 cpb_status cpb_bowe_hopwood_crh_batch(cpb_bowe_hopwood_ctx* c, const uint8_t* in, size_t len, size_t stride, uint64_t* out_x, size_t n) {
+    return cpb::guarded([&]() -> cpb_status {
     if (!c) return fail(CPB_NULL_POINTER, "null context");
     if (len * 8 > c->n_gens * 3)
         return fail(CPB_BAD_LENGTH, "incorrect input bitlength %zu for window params %dx%dx3", len * 8, c->window_size, c->num_windows);
@@ -1039,8 +1074,10 @@ cpb_status cpb_bowe_hopwood_crh_batch(cpb_bowe_hopwood_ctx* c, const uint8_t* in
     CPB_CUDA(cudaMemcpyAsync(out_x, c->s_out.ptr, n * 32, cudaMemcpyDeviceToHost, c->stream));
     CPB_CUDA(cudaStreamSynchronize(c->stream));
     return CPB_OK;
+    });
 }
 cpb_status cpb_bowe_hopwood_two_to_one_batch(cpb_bowe_hopwood_ctx* c, const uint64_t* children_x, uint64_t* out_x, size_t n) {
+    return cpb::guarded([&]() -> cpb_status {
     if (!c) return fail(CPB_NULL_POINTER, "null context");
     if (n == 0) return CPB_OK;
     if (!children_x || !out_x) return fail(CPB_NULL_POINTER, "null buffer");
@@ -1054,6 +1091,7 @@ cpb_status cpb_bowe_hopwood_two_to_one_batch(cpb_bowe_hopwood_ctx* c, const uint
     CPB_CUDA(cudaMemcpyAsync(out_x, c->s_out.ptr, n * 32, cudaMemcpyDeviceToHost, c->stream));
     CPB_CUDA(cudaStreamSynchronize(c->stream));
     return CPB_OK;
+    });
 }
 
 }  // extern "C"

@@ -290,11 +290,13 @@ int cpb_device_count(void) {
 }
 
 cpb_status cpb_field_modulus(int field_id, uint64_t out[4]) {
+    return cpb::guarded([&]() -> cpb_status {
     const uint64_t* m = host::field_modulus(field_id);
     if (!m) return fail(CPB_BAD_PARAMS, "unknown field id %d", field_id);
     if (!out) return fail(CPB_NULL_POINTER, "null out");
     memcpy(out, m, 32);
     return CPB_OK;
+    });
 }
 
 static cpb_status field_convert(int field_id, int device, const uint64_t* in, uint64_t* out, size_t n, int to_mont) {
@@ -322,14 +324,19 @@ static cpb_status field_convert(int field_id, int device, const uint64_t* in, ui
     return CPB_OK;
 }
 cpb_status cpb_field_to_montgomery(int field_id, int device, const uint64_t* in, uint64_t* out, size_t n) {
+    return cpb::guarded([&]() -> cpb_status {
     return field_convert(field_id, device, in, out, n, 1);
+    });
 }
 cpb_status cpb_field_from_montgomery(int field_id, int device, const uint64_t* in, uint64_t* out, size_t n) {
+    return cpb::guarded([&]() -> cpb_status {
     return field_convert(field_id, device, in, out, n, 0);
+    });
 }
 
 cpb_status cpb_poseidon_find_ark_and_mds(int field_id, uint64_t prime_bits, int rate, int full_rounds,
                                          int partial_rounds, int skip_matrices, uint64_t* ark_out, uint64_t* mds_out) {
+    return cpb::guarded([&]() -> cpb_status {
     const uint64_t* mod = host::field_modulus(field_id);
     if (!mod) return fail(CPB_BAD_PARAMS, "unknown field id %d", field_id);
     if (!ark_out || !mds_out) return fail(CPB_NULL_POINTER, "null output");
@@ -344,10 +351,12 @@ cpb_status cpb_poseidon_find_ark_and_mds(int field_id, uint64_t prime_bits, int 
     memcpy(ark_out, ark.data(), ark.size() * 32);
     memcpy(mds_out, mds.data(), mds.size() * 32);
     return CPB_OK;
+    });
 }
 
 cpb_status cpb_poseidon_default_entry(int rate, int optimized_for_weights, uint64_t* alpha, int* full_rounds,
                                       int* partial_rounds, int* skip_matrices) {
+    return cpb::guarded([&]() -> cpb_status {
     host::DefaultEntry e;
     if (!host::default_entry(rate, optimized_for_weights != 0, e))
         return fail(CPB_BAD_PARAMS, "no default entry for rate %d", rate);   // reference returns None
@@ -356,11 +365,13 @@ cpb_status cpb_poseidon_default_entry(int rate, int optimized_for_weights, uint6
     if (partial_rounds) *partial_rounds = e.rp;
     if (skip_matrices) *skip_matrices = e.skip;
     return CPB_OK;
+    });
 }
 
 cpb_status cpb_poseidon_ctx_create(int field_id, int rate, int capacity, int full_rounds, int partial_rounds,
                                    uint64_t alpha, const uint64_t* ark, const uint64_t* mds, int device,
                                    cpb_poseidon_ctx** out) {
+    return cpb::guarded([&]() -> cpb_status {
     if (!out) return fail(CPB_NULL_POINTER, "null out");
     *out = nullptr;
     const uint64_t* mod = host::field_modulus(field_id);
@@ -407,6 +418,7 @@ cpb_status cpb_poseidon_ctx_create(int field_id, int rate, int capacity, int ful
     }
     *out = c;
     return CPB_OK;
+    });
 }
 
 void cpb_poseidon_ctx_destroy(cpb_poseidon_ctx* c) {
@@ -426,25 +438,32 @@ int cpb_poseidon_ctx_device(const cpb_poseidon_ctx* c) { return c ? c->device : 
 
 // ---- device-pointer entry points
 cpb_status cpb_poseidon_permute_batch_dev(cpb_poseidon_ctx* c, const uint64_t* in, uint64_t* out, size_t n, void* stream) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(check_ctx(c));
     DeviceGuard g(c->device);
     return launch_permute(c, (const u32*)in, (u32*)out, n, (cudaStream_t)stream);
+    });
 }
 cpb_status cpb_poseidon_crh_batch_dev(cpb_poseidon_ctx* c, const uint64_t* in, size_t len, uint64_t* out, size_t n, void* stream) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(check_ctx(c));
     DeviceGuard g(c->device);
     return launch_crh(c, (const u32*)in, len, (u32*)out, n, (cudaStream_t)stream);
+    });
 }
 cpb_status cpb_poseidon_sponge_batch_dev(cpb_poseidon_ctx* c, const uint64_t* in, size_t len, uint64_t* out, size_t n_squeeze,
                                          size_t n, void* stream) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(check_ctx(c));
     DeviceGuard g(c->device);
     return launch_crh(c, (const u32*)in, len, (u32*)out, n, (cudaStream_t)stream, n_squeeze);
+    });
 }
 cpb_status cpb_merkle_poseidon_verify_batch_dev(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, const uint64_t* root,
                                                 const uint64_t* leaves, size_t leaf_len, const uint64_t* leaf_sibling_hashes,
                                                 const uint64_t* auth_paths, size_t path_len, const uint64_t* leaf_indexes,
                                                 uint8_t* ok, size_t n, void* stream) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(check_ctx(leaf));
     CPB_TRY(check_ctx(node));
     if (leaf->device != node->device || leaf->field_id != node->field_id || leaf->dev.t != node->dev.t)
@@ -454,25 +473,31 @@ cpb_status cpb_merkle_poseidon_verify_batch_dev(cpb_poseidon_ctx* leaf, cpb_pose
     DeviceGuard g(leaf->device);
     return launch_verify(leaf, node, (const u32*)root, (const u32*)leaves, leaf_len, (const u32*)leaf_sibling_hashes,
                          (const u32*)auth_paths, (int)path_len, (const unsigned long long*)leaf_indexes, ok, n, (cudaStream_t)stream);
+    });
 }
 cpb_status cpb_poseidon_compress_batch_dev(cpb_poseidon_ctx* c, const uint64_t* pairs, uint64_t* out, size_t n, void* stream) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(check_ctx(c));
     if (c->dev.rate < 2)   // two absorbs then one squeeze = one permutation only when rate >= 2
         return fail(CPB_UNSUPPORTED, "two-to-one with rate < 2 not supported");
     DeviceGuard g(c->device);
     return launch_crh(c, (const u32*)pairs, 2, (u32*)out, n, (cudaStream_t)stream);
+    });
 }
 cpb_status cpb_merkle_poseidon_from_digests_dev(cpb_poseidon_ctx* node, const uint64_t* leaf_digests, size_t n,
                                                 uint64_t* non_leaf_nodes, void* stream) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(check_ctx(node));
     if (!pow2_gt1(n)) return fail(CPB_NOT_POW2, "leaves.len() should be power of two and greater than one (got %zu)", n);
     if (node->dev.rate < 2) return fail(CPB_UNSUPPORTED, "two-to-one with rate < 2 not supported");
     DeviceGuard g(node->device);
     return merkle_build_streams(node, node, nullptr, 0, n, (u32*)leaf_digests, (u32*)non_leaf_nodes, (cudaStream_t)stream);
+    });
 }
 cpb_status cpb_merkle_poseidon_build_dev(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, const uint64_t* leaves,
                                          size_t leaf_len, size_t n, uint64_t* leaf_nodes, uint64_t* non_leaf_nodes,
                                          void* stream) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(check_ctx(leaf));
     CPB_TRY(check_ctx(node));
     if (leaf->device != node->device || leaf->field_id != node->field_id)
@@ -482,6 +507,7 @@ cpb_status cpb_merkle_poseidon_build_dev(cpb_poseidon_ctx* leaf, cpb_poseidon_ct
     DeviceGuard g(leaf->device);
     return merkle_build_streams(leaf, node, (const u32*)leaves, leaf_len, n, (u32*)leaf_nodes, (u32*)non_leaf_nodes,
                                 (cudaStream_t)stream);
+    });
 }
 
 // ---- host-pointer entry points: H2D, launch, D2H on the context stream
@@ -503,13 +529,18 @@ static cpb_status host_roundtrip_crh(cpb_poseidon_ctx* c, const uint64_t* in, si
     return CPB_OK;
 }
 cpb_status cpb_poseidon_permute_batch(cpb_poseidon_ctx* c, const uint64_t* in, uint64_t* out, size_t n) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(check_ctx(c));
     return host_roundtrip_crh(c, in, (size_t)c->dev.t, 0, out, (size_t)c->dev.t, n, 1);
+    });
 }
 cpb_status cpb_poseidon_crh_batch(cpb_poseidon_ctx* c, const uint64_t* in, size_t len, uint64_t* out, size_t n) {
+    return cpb::guarded([&]() -> cpb_status {
     return host_roundtrip_crh(c, in, len, len, out, 1, n, 0);
+    });
 }
 cpb_status cpb_poseidon_sponge_batch(cpb_poseidon_ctx* c, const uint64_t* in, size_t len, uint64_t* out, size_t n_squeeze, size_t n) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(check_ctx(c));
     if (n == 0 || n_squeeze == 0) return CPB_OK;
     if ((!in && len) || !out) return fail(CPB_NULL_POINTER, "null buffer");
@@ -523,11 +554,13 @@ cpb_status cpb_poseidon_sponge_batch(cpb_poseidon_ctx* c, const uint64_t* in, si
     CPB_CUDA(cudaMemcpyAsync(out, c->s_out.ptr, out_b, cudaMemcpyDeviceToHost, c->stream));
     CPB_CUDA(cudaStreamSynchronize(c->stream));
     return CPB_OK;
+    });
 }
 cpb_status cpb_merkle_poseidon_verify_batch(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, const uint64_t* root,
                                             const uint64_t* leaves, size_t leaf_len, const uint64_t* leaf_sibling_hashes,
                                             const uint64_t* auth_paths, size_t path_len, const uint64_t* leaf_indexes, uint8_t* ok,
                                             size_t n) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(check_ctx(leaf));
     CPB_TRY(check_ctx(node));
     if (n == 0) return CPB_OK;
@@ -554,15 +587,19 @@ cpb_status cpb_merkle_poseidon_verify_batch(cpb_poseidon_ctx* leaf, cpb_poseidon
     CPB_CUDA(cudaMemcpyAsync(ok, leaf->s_out.ptr, n, cudaMemcpyDeviceToHost, st));
     CPB_CUDA(cudaStreamSynchronize(st));
     return CPB_OK;
+    });
 }
 cpb_status cpb_poseidon_compress_batch(cpb_poseidon_ctx* c, const uint64_t* pairs, uint64_t* out, size_t n) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(check_ctx(c));
     if (c->dev.rate < 2) return fail(CPB_UNSUPPORTED, "two-to-one with rate < 2 not supported");
     return host_roundtrip_crh(c, pairs, 2, 2, out, 1, n, 0);
+    });
 }
 
 cpb_status cpb_merkle_poseidon_from_digests(cpb_poseidon_ctx* node, const uint64_t* leaf_digests, size_t n,
                                             uint64_t* non_leaf_nodes) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(check_ctx(node));
     if (!pow2_gt1(n)) return fail(CPB_NOT_POW2, "leaves.len() should be power of two and greater than one (got %zu)", n);
     if (!leaf_digests || !non_leaf_nodes) return fail(CPB_NULL_POINTER, "null buffer");
@@ -575,10 +612,12 @@ cpb_status cpb_merkle_poseidon_from_digests(cpb_poseidon_ctx* node, const uint64
     CPB_CUDA(cudaMemcpyAsync(non_leaf_nodes, node->s_out.ptr, (n - 1) * 32, cudaMemcpyDeviceToHost, node->stream));
     CPB_CUDA(cudaStreamSynchronize(node->stream));
     return CPB_OK;
+    });
 }
 
 cpb_status cpb_merkle_poseidon_build(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, const uint64_t* leaves,
                                      size_t leaf_len, size_t n, uint64_t* leaf_nodes, uint64_t* non_leaf_nodes) {
+    return cpb::guarded([&]() -> cpb_status {
     CPB_TRY(check_ctx(leaf));
     CPB_TRY(check_ctx(node));
     if (!pow2_gt1(n)) return fail(CPB_NOT_POW2, "leaves.len() should be power of two and greater than one (got %zu)", n);
@@ -598,6 +637,7 @@ cpb_status cpb_merkle_poseidon_build(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* n
     CPB_TRY(merkle_build_streams(leaf, node, (const u32*)leaf->s_in.ptr, leaf_len, n, (u32*)leaf->s_out.ptr, (u32*)leaf->s_aux.ptr, st, &H));
     CPB_CUDA(cudaStreamSynchronize(st));
     return CPB_OK;
+    });
 }
 
 }  // extern "C"

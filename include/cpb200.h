@@ -49,7 +49,8 @@ typedef enum cpb_status {
     CPB_CUDA_ERROR = 4,
     CPB_NO_DEVICE = 5,
     CPB_UNSUPPORTED = 6,
-    CPB_NULL_POINTER = 7
+    CPB_NULL_POINTER = 7,
+    CPB_INTERNAL_ERROR = 8   /* host allocation failure or any C++ exception caught at the boundary */
 } cpb_status;
 
 typedef enum cpb_field {
