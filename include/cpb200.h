@@ -21,7 +21,8 @@
  * device) plus a CUDA stream handle (`cudaStream_t` passed as void*, NULL = default stream),
  * launch asynchronously and do not synchronise.
  *
- * ERRORS.  Every function returns a cpb_status.  Nothing panics/throws across the ABI; the
+ * ERRORS.  Every function returns a cpb_status.  Nothing panics/throws across the ABI (each entry point runs under an
+ * exception guard: host allocation failures and the like come back as CPB_INTERNAL_ERROR); the
  * shim maps codes back to the reference's behaviour (R/lib.rs:46-52 `Error`, and the panics at
  * R/crh/pedersen/mod.rs:82-89, R/merkle_tree/mod.rs:430-433).  cpb_last_error() returns a
  * thread-local description of the last failure.  There is NO CPU fallback: without a usable
