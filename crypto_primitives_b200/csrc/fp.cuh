@@ -345,35 +345,43 @@ template <class F> CPB_HD void redc_row_shift_x(u32* E, u32* O, u32& X, u32 tin,
     X = addc(xn, 0u);
 }
 
-// V += a * bi   (no shift)
-CPB_HD void acc_row_x(u32* E, u32* O, u32& X, const u32* a, u32 bi) {
+// V += a * bi   (no shift).  WX: keep the overflow word X up to date (see fp_dot for when it is needed).
+template <bool WX> CPB_HD void acc_row_x(u32* E, u32* O, u32& X, const u32* a, u32 bi) {
     mad_wide_cc(O[0], O[1], a[1], bi);
     madc_wide_cc(O[2], O[3], a[3], bi);
     madc_wide_cc(O[4], O[5], a[5], bi);
     madc_wide_cc(O[6], O[7], a[7], bi);
-    X = addc(X, 0);
+    if (WX) X = addc(X, 0);
     mad_wide_cc(E[0], E[1], a[0], bi);
     madc_wide_cc(E[2], E[3], a[2], bi);
     madc_wide_cc(E[4], E[5], a[4], bi);
     madc_wide_cc(E[6], E[7], a[6], bi);
-    O[7] = addc_cc(O[7], 0);
-    X = addc(X, 0);
+    if (WX) {
+        O[7] = addc_cc(O[7], 0);
+        X = addc(X, 0);
+    } else {
+        O[7] = addc(O[7], 0);
+    }
 }
 
 // V = V/2^32 + a * bi  (E/O are the swapped accumulators, see next_row)
-CPB_HD void shift_acc_row_x(u32* E, u32* O, u32& X, const u32* a, u32 bi) {
+template <bool WX> CPB_HD void shift_acc_row_x(u32* E, u32* O, u32& X, const u32* a, u32 bi) {
     E[0] = add_cc(E[0], O[1]);
     madc_wide_cc_from(O[0], O[1], a[1], bi, O[2], O[3]);
     madc_wide_cc_from(O[2], O[3], a[3], bi, O[4], O[5]);
     madc_wide_cc_from(O[4], O[5], a[5], bi, O[6], O[7]);
     madc_wide_end(O[6], O[7], a[7], bi);
-    O[7] += X;   // old overflow limb lands on the new top limb; cannot overflow (V/2^32 < 2^288)
+    if (WX) O[7] += X;   // old overflow limb lands on the new top limb; cannot overflow (V/2^32 < 2^288)
     mad_wide_cc(E[0], E[1], a[0], bi);
     madc_wide_cc(E[2], E[3], a[2], bi);
     madc_wide_cc(E[4], E[5], a[4], bi);
     madc_wide_cc(E[6], E[7], a[6], bi);
-    O[7] = addc_cc(O[7], 0);
-    X = addc(0, 0);
+    if (WX) {
+        O[7] = addc_cc(O[7], 0);
+        X = addc(0, 0);
+    } else {
+        O[7] = addc(O[7], 0);
+    }
 }
 
 // limb i (0..8) of p << k
@@ -396,7 +404,16 @@ template <class F, int K> CPB_HD void reduce9(u32* r) {
     }
 }
 
+// The running value of a T-term dot product stays below (T+1) * p * 2^32.  When (T+1) * p < 2^256 that fits the 9 limbs
+// of (E, O) and the overflow word is dead weight: 5 ALU instructions per row.  True for BN254 Fr (254 bits) up to T = 3,
+// BLS12-377 Fr up to 7, Jubjub Fr up to 15; BLS12-381 Fr (255 bits) needs X from T = 2.
+template <class F, int T> CPB_HD constexpr bool dot_needs_x() {
+    constexpr int slack = 8 * LIMB_BITS - F::BITS;      // (T+1) * p < 2^(8*LIMB_BITS)  <=  T + 1 <= 2^slack
+    return slack < 30 && (T + 1) > (1 << (slack < 30 ? slack : 0));
+}
+
 template <class F, int T, int I> CPB_HD void dot_row(u32* E, u32* O, u32& X, const u32 (&a)[T][8], const u32* b, const u32* pm) {
+    constexpr bool WX = dot_needs_x<F, T>();
     // b: T constants of 8 limbs each (shared memory); this row uses limb I of each
     if (I == 0) {
         u32 bi = b[0];
@@ -406,11 +423,12 @@ template <class F, int T, int I> CPB_HD void dot_row(u32* E, u32* O, u32& X, con
             mul_wide(O[j], O[j + 1], a[0][j + 1], bi);
         }
     } else {
-        shift_acc_row_x(E, O, X, a[0], b[I]);
+        shift_acc_row_x<WX>(E, O, X, a[0], b[I]);
     }
 #pragma unroll
-    for (int t = 1; t < T; t++) acc_row_x(E, O, X, a[t], b[8 * t + I]);
-    redc_row_x<F>(E, O, X, pm);
+    for (int t = 1; t < T; t++) acc_row_x<WX>(E, O, X, a[t], b[8 * t + I]);
+    if (WX) redc_row_x<F>(E, O, X, pm);
+    else redc_row<F>(E, O, pm);
 }
 
 }  // namespace detail
