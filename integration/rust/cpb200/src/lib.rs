@@ -74,6 +74,7 @@ macro_rules! gpu_field {
 gpu_field!(ark_bls12_381::FrConfig, 0);
 gpu_field!(ark_bn254::FrConfig, 1);
 gpu_field!(ark_ed_on_bls12_381::FrConfig, 2);
+// ark_ed_on_bls12_381::Fq is ark_bls12_381::Fr (the Jubjub base field): already covered by id 0.
 
 fn flatten<F: GpuField>(xs: &[F]) -> Vec<u64> { xs.iter().flat_map(|x| x.mont_limbs()).collect() }
 fn unflatten<F: GpuField>(l: &[u64]) -> Vec<F> { l.chunks_exact(4).map(|c| F::from_mont_limbs([c[0], c[1], c[2], c[3]])).collect() }
@@ -179,5 +180,121 @@ impl<F: GpuField> GpuMerkleTree<F> {
         }
         path.reverse();
         path
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Pedersen CRH / commitment over Jubjub (`ark_ed_on_bls12_381::EdwardsProjective`, curve id 0 of the library).
+// ------------------------------------------------------------------------------------------------------------------
+pub mod pedersen {
+    use super::{check, GpuField};
+    use ark_crypto_primitives::commitment::{pedersen as ref_comm, CommitmentScheme};
+    use ark_crypto_primitives::crh::{pedersen as ref_crh, CRHScheme};
+    use ark_crypto_primitives::Error;
+    use ark_ec::CurveGroup;
+    use ark_ed_on_bls12_381::{EdwardsAffine, EdwardsProjective, Fq};
+    use ark_ff::{BigInteger, PrimeField};
+    use ark_std::{borrow::Borrow, marker::PhantomData, rand::Rng, sync::Arc};
+    use std::os::raw::c_int;
+
+    #[allow(non_camel_case_types)]
+    #[repr(C)]
+    pub struct cpb_pedersen_ctx {
+        _private: [u8; 0],
+    }
+    extern "C" {
+        fn cpb_pedersen_ctx_create(curve_id: c_int, window_size: c_int, num_windows: c_int, generators_xy: *const u64, n_rand: usize,
+                                   rand_generators_xy: *const u64, device: c_int, out: *mut *mut cpb_pedersen_ctx) -> c_int;
+        fn cpb_pedersen_ctx_destroy(ctx: *mut cpb_pedersen_ctx);
+        fn cpb_pedersen_crh_batch(ctx: *mut cpb_pedersen_ctx, input: *const u8, len: usize, stride: usize, out_xy: *mut u64, n: usize) -> c_int;
+        fn cpb_pedersen_commit_batch(ctx: *mut cpb_pedersen_ctx, input: *const u8, len: usize, stride: usize, randomness_le32: *const u8,
+                                     out_xy: *mut u64, n: usize) -> c_int;
+    }
+
+    struct Ctx(*mut cpb_pedersen_ctx);
+    unsafe impl Send for Ctx {}
+    unsafe impl Sync for Ctx {}
+    impl Drop for Ctx {
+        fn drop(&mut self) { unsafe { cpb_pedersen_ctx_destroy(self.0) } }
+    }
+
+    fn xy(points: &[EdwardsProjective]) -> Vec<u64> {
+        // Parameters.generators holds projective points (R/crh/pedersen/mod.rs:28-31); the ABI takes affine x, y limbs
+        EdwardsProjective::normalize_batch(points).iter().flat_map(|p| [p.x.mont_limbs(), p.y.mont_limbs()].concat()).collect()
+    }
+    fn points(limbs: &[u64]) -> Vec<EdwardsAffine> {
+        limbs.chunks_exact(8)
+            .map(|c| EdwardsAffine::new_unchecked(Fq::from_mont_limbs([c[0], c[1], c[2], c[3]]), Fq::from_mont_limbs([c[4], c[5], c[6], c[7]])))
+            .collect()
+    }
+
+    /// `pedersen::Parameters<C>` (+ the commitment's `randomness_generator`) and the device tables built from them.
+    #[derive(Clone)]
+    pub struct GpuPedersenParams {
+        pub generators: Vec<Vec<EdwardsProjective>>,
+        pub randomness_generator: Vec<EdwardsProjective>,
+        ctx: Arc<Ctx>,
+    }
+    impl GpuPedersenParams {
+        pub fn from_crh<W: ref_crh::Window>(p: &ref_crh::Parameters<EdwardsProjective>, device: i32) -> Result<Self, Error> {
+            Self::build::<W>(p.generators.clone(), Vec::new(), device)
+        }
+        pub fn from_commitment<W: ref_crh::Window>(p: &ref_comm::Parameters<EdwardsProjective>, device: i32) -> Result<Self, Error> {
+            Self::build::<W>(p.generators.clone(), p.randomness_generator.clone(), device)
+        }
+        fn build<W: ref_crh::Window>(generators: Vec<Vec<EdwardsProjective>>, randomness_generator: Vec<EdwardsProjective>, device: i32)
+                                     -> Result<Self, Error> {
+            let flat: Vec<EdwardsProjective> = generators.iter().flatten().cloned().collect();
+            let (g, r) = (xy(&flat), xy(&randomness_generator));
+            let mut raw = core::ptr::null_mut();
+            check(unsafe {
+                cpb_pedersen_ctx_create(0, W::WINDOW_SIZE as c_int, W::NUM_WINDOWS as c_int, g.as_ptr(), randomness_generator.len(),
+                                        if r.is_empty() { core::ptr::null() } else { r.as_ptr() }, device, &mut raw)
+            })?;
+            Ok(Self { generators, randomness_generator, ctx: Arc::new(Ctx(raw)) })
+        }
+    }
+
+    /// `crh::pedersen::CRH<EdwardsProjective, W>` (R/crh/pedersen/mod.rs:58-130).
+    pub struct GpuPedersenCRH<W>(PhantomData<W>);
+    impl<W: ref_crh::Window> GpuPedersenCRH<W> {
+        /// n inputs of `len` bytes each, contiguous.
+        pub fn evaluate_batch(p: &GpuPedersenParams, inputs: &[u8], len: usize) -> Result<Vec<EdwardsAffine>, Error> {
+            let n = if len == 0 { 0 } else { inputs.len() / len };
+            let mut out = vec![0u64; 8 * n];
+            check(unsafe { cpb_pedersen_crh_batch(p.ctx.0, inputs.as_ptr(), len, len, out.as_mut_ptr(), n) })?;
+            Ok(points(&out))
+        }
+    }
+    impl<W: ref_crh::Window> CRHScheme for GpuPedersenCRH<W> {
+        type Input = [u8];
+        type Output = EdwardsAffine;
+        type Parameters = GpuPedersenParams;
+        fn setup<R: Rng>(rng: &mut R) -> Result<Self::Parameters, Error> {
+            GpuPedersenParams::from_crh::<W>(&ref_crh::CRH::<EdwardsProjective, W>::setup(rng)?, 0)
+        }
+        fn evaluate<T: Borrow<[u8]>>(p: &Self::Parameters, input: T) -> Result<EdwardsAffine, Error> {
+            let input = input.borrow();
+            let mut out = [0u64; 8];
+            check(unsafe { cpb_pedersen_crh_batch(p.ctx.0, input.as_ptr(), input.len(), input.len(), out.as_mut_ptr(), 1) })?;
+            Ok(points(&out)[0])
+        }
+    }
+
+    /// `commitment::pedersen::Commitment<EdwardsProjective, W>` (R/commitment/pedersen/mod.rs:38-106).
+    pub struct GpuPedersenCommitment<W>(PhantomData<W>);
+    impl<W: ref_crh::Window> CommitmentScheme for GpuPedersenCommitment<W> {
+        type Parameters = GpuPedersenParams;
+        type Randomness = ref_comm::Randomness<EdwardsProjective>;
+        type Output = EdwardsAffine;
+        fn setup<R: Rng>(rng: &mut R) -> Result<Self::Parameters, Error> {
+            GpuPedersenParams::from_commitment::<W>(&ref_comm::Commitment::<EdwardsProjective, W>::setup(rng)?, 0)
+        }
+        fn commit(p: &Self::Parameters, input: &[u8], randomness: &Self::Randomness) -> Result<EdwardsAffine, Error> {
+            let r = randomness.0.into_bigint().to_bytes_le();          // the bits R/commitment/pedersen/mod.rs:93 iterates, 32 bytes
+            let mut out = [0u64; 8];
+            check(unsafe { cpb_pedersen_commit_batch(p.ctx.0, input.as_ptr(), input.len(), input.len(), r.as_ptr(), out.as_mut_ptr(), 1) })?;
+            Ok(points(&out)[0])
+        }
     }
 }
