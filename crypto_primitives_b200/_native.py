@@ -19,6 +19,7 @@ CPB_OK, CPB_BAD_LENGTH, CPB_BAD_PARAMS, CPB_NOT_POW2, CPB_CUDA_ERROR, CPB_NO_DEV
 # name -> (restype, argtypes); mirrors include/cpb200.h one to one (tests/test_abi.py checks it).
 SIGNATURES = {
     "cpb_last_error": (C.c_char_p, []),
+    "cpb_abi_version": (C.c_int, []),
     "cpb_version": (C.c_int, []),
     "cpb_device_count": (C.c_int, []),
     "cpb_field_modulus": (C.c_int, [C.c_int, u64p]),

@@ -276,6 +276,7 @@ bool pow2_gt1(size_t n) { return n > 1 && (n & (n - 1)) == 0; }
 extern "C" {
 
 const char* cpb_last_error(void) { return last_error_ref().c_str(); }
+int cpb_abi_version(void) { return CPB_ABI_VERSION; }
 int cpb_version(void) { return 100; }
 
 int cpb_device_count(void) {

@@ -72,6 +72,10 @@ typedef struct cpb_pedersen_ctx cpb_pedersen_ctx;
 typedef struct cpb_bowe_hopwood_ctx cpb_bowe_hopwood_ctx;
 
 const char* cpb_last_error(void);
+
+/* ABI revision of this header: bumped when entry points or status codes are added (2 = CPB_INTERNAL_ERROR, cpb_abi_version). */
+#define CPB_ABI_VERSION 2
+int cpb_abi_version(void);
 int cpb_version(void);
 /* Number of visible CUDA devices with compute capability 10.x (0 when none / no driver). */
 int cpb_device_count(void);
