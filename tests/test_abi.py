@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert N.lib.cpb_abi_version() == int(re.search(r"#define CPB_ABI_VERSION (\d+)", hdr).group(1))
     # the status codes of the header and of the ctypes binding agree
     status_enum = hdr[hdr.index("typedef enum cpb_status"):hdr.index("} cpb_status;")]
-    codes = dict(re.findall(r"(CPB_[A-Z_]+) = (\d+)", status_enum))
+    codes = dict(re.findall(r"(CPB_[A-Z0-9_]+) = (\d+)", status_enum))
     assert len(codes) == 9
     for name, value in codes.items():
         assert getattr(N, name) == int(value), name
