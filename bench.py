@@ -158,6 +158,35 @@ def cpu_baseline(field_key, leaf_len, threads, log_sample):
     return perms / dt, dt, perms
 
 
+def config1_probe():
+    """BASELINE configs[0] -- the reference's own CPU-runnable case: crh::poseidon::CRH::evaluate on 1024 inputs of two
+    BLS12-381 Fr elements (default rate-2 parameters).  CPU: the C restatement on ONE thread, as that config is stated;
+    GPU: the host-pointer C-ABI call (copies included), median of 20.  Outputs compared."""
+    import ctypes as C
+    import numpy as np
+    import crypto_primitives_b200 as cp
+    from crypto_primitives_b200 import _native as N
+    from oracle import cref
+    ocfg, P = oracle_poseidon("bls")
+    x = cref.synth_field_mont(0xB2000001, 1024 * 2, ocfg.p).reshape(1024, 2, 4)
+    t0 = time.perf_counter()
+    exp = P.crh_batch(x, threads=1)
+    cpu_dt = time.perf_counter() - t0
+    cfg = cp.get_default_poseidon_parameters(cp.BLS12_381_FR, 2, False)
+    ctx = cfg.context(0)
+    out = np.empty((1024, 4), dtype=np.uint64)
+    times = []
+    for _ in range(23):
+        t0 = time.perf_counter()
+        N.check(N.lib.cpb_poseidon_crh_batch(ctx, x.ctypes.data_as(N.u64p), 2, out.ctypes.data_as(N.u64p), 1024))
+        times.append(time.perf_counter() - t0)
+    gpu_dt = statistics.median(times[3:])
+    return {"workload": "crh::poseidon::CRH::evaluate, BLS12-381 Fr, 1024 inputs x 2 elements",
+            "cpu_single_thread": {"hashes_per_s": 1024 / cpu_dt, "ms": 1e3 * cpu_dt, "kind": "port"},
+            "gpu_host_call": {"hashes_per_s": 1024 / gpu_dt, "ms": 1e3 * gpu_dt, "api": "cpb_poseidon_crh_batch (pageable host pointers, copies included)"},
+            "outputs_equal": bool(np.array_equal(out, exp))}
+
+
 def run_reference(args):
     """--impl reference: the CPU arm, on rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -328,6 +357,11 @@ def run_b200(args):
                 "roofline": roofline, "integer_pipe": integer,
                 "cpu_baseline": {"value": cpu_v, "unit": "perms/s", "cores": threads, "kind": "port",
                                  "sample": f"2^{min(logn, 18)}-leaf tree of the same shape ({cpu_perms} permutations, {cpu_dt:.2f} s wall)"}}
+        if world == 1:
+            try:
+                line["config1"] = config1_probe()
+            except Exception as e:                      # an extra, never a reason to lose the contract line
+                line["config1"] = {"error": repr(e)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
