@@ -40,6 +40,9 @@ def lib():
         L.oref_field_free.argtypes = [C.c_void_p]
         L.oref_to_mont.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t]
         L.oref_from_mont.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t]
+        L.oref_fe_mul_batch.argtypes = [C.c_void_p, u64p, u64p, u64p, C.c_size_t]
+        L.oref_fe_sqr_batch.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t]
+        L.oref_fe_addsub_batch.argtypes = [C.c_void_p, u64p, u64p, u64p, u64p, C.c_size_t]
         L.oref_poseidon_new.restype = C.c_void_p
         L.oref_poseidon_new.argtypes = [u64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, u64p, u64p]
         L.oref_poseidon_free.argtypes = [C.c_void_p]
@@ -90,6 +93,19 @@ def ints_to_mont(vals, p: int) -> np.ndarray:
 def mont_to_ints(arr: np.ndarray, p: int) -> list[int]:
     a = np.asarray(arr, dtype=np.uint64).reshape(-1, 4)
     return [F.from_mont(F.from_limbs(row), p) for row in a]
+
+
+def field_ops(p: int, a: np.ndarray, b: np.ndarray):
+    """Element-wise (a*b/R, a*a/R, a+b, a-b) mod p on (n,4) limb arrays through the C oracle's field routines."""
+    a = np.ascontiguousarray(a, dtype=np.uint64); b = np.ascontiguousarray(b, dtype=np.uint64)
+    n = a.shape[0]
+    fld = lib().oref_field_new(_p(limbs(p)))
+    mul, sqr, add, sub = (np.empty_like(a) for _ in range(4))
+    lib().oref_fe_mul_batch(fld, _p(mul), _p(a), _p(b), n)
+    lib().oref_fe_sqr_batch(fld, _p(sqr), _p(a), n)
+    lib().oref_fe_addsub_batch(fld, _p(add), _p(sub), _p(a), _p(b), n)
+    lib().oref_field_free(fld)
+    return mul, sqr, add, sub
 
 
 def synth_field_mont(seed: int, n: int, p: int) -> np.ndarray:

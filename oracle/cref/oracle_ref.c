@@ -22,6 +22,7 @@
  * oracle (tests/test_oracle_*.py check C == Python == KAT).  Pedersen / Merkle:
  * PARITY UNPINNED (no golden vectors exist in the reference).
  */
+#include <immintrin.h>
 #include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -37,11 +38,12 @@ typedef struct {
     u64 ninv;      /* -p^{-1} mod 2^64 */
     fe one;        /* R mod p */
     fe r2;         /* R^2 mod p */
+    int nocarry;   /* top bit of p clear: fe_mul may drop the carry word */
 } field_t;
 
 /* ---------------------------------------------------------------- field */
 
-static int ge4(const u64 a[4], const u64 b[4]) {
+static inline int ge4(const u64 a[4], const u64 b[4]) {
     for (int i = 3; i >= 0; i--) {
         if (a[i] > b[i]) return 1;
         if (a[i] < b[i]) return 0;
@@ -49,48 +51,54 @@ static int ge4(const u64 a[4], const u64 b[4]) {
     return 1;
 }
 
-static u64 sub4(u64 r[4], const u64 a[4], const u64 b[4]) {
-    u64 borrow = 0;
-    for (int i = 0; i < 4; i++) {
-        u128 d = (u128)a[i] - b[i] - borrow;
-        r[i] = (u64)d;
-        borrow = (u64)(d >> 64) & 1;
-    }
-    return borrow;
+static inline u64 sub4(u64 r[4], const u64 a[4], const u64 b[4]) {
+    unsigned long long t;
+    unsigned char bw = _subborrow_u64(0, a[0], b[0], &t); r[0] = t;
+    bw = _subborrow_u64(bw, a[1], b[1], &t); r[1] = t;
+    bw = _subborrow_u64(bw, a[2], b[2], &t); r[2] = t;
+    bw = _subborrow_u64(bw, a[3], b[3], &t); r[3] = t;
+    return bw;
 }
 
-static u64 add4(u64 r[4], const u64 a[4], const u64 b[4]) {
-    u64 c = 0;
-    for (int i = 0; i < 4; i++) {
-        u128 s = (u128)a[i] + b[i] + c;
-        r[i] = (u64)s;
-        c = (u64)(s >> 64);
-    }
+static inline u64 add4(u64 r[4], const u64 a[4], const u64 b[4]) {
+    unsigned long long t;
+    unsigned char c = _addcarry_u64(0, a[0], b[0], &t); r[0] = t;
+    c = _addcarry_u64(c, a[1], b[1], &t); r[1] = t;
+    c = _addcarry_u64(c, a[2], b[2], &t); r[2] = t;
+    c = _addcarry_u64(c, a[3], b[3], &t); r[3] = t;
     return c;
 }
 
-static void fe_add(const field_t *F, fe *r, const fe *a, const fe *b) {
-    u64 t[4];
+/* a + b mod p, a - b mod p: add/sub then one conditional correction, branch-free (what ark-ff's add_assign /
+ * sub_assign + subtract_modulus do with a data-dependent branch; same values). */
+static inline void fe_add(const field_t *F, fe *r, const fe *a, const fe *b) {
+    u64 t[4], d[4];
     u64 c = add4(t, a->l, b->l);
-    if (c || ge4(t, F->p)) sub4(t, t, F->p);
-    memcpy(r->l, t, 32);
+    u64 bw = sub4(d, t, F->p);
+    int keep = !c && bw;                      /* t < p: keep t */
+    for (int i = 0; i < 4; i++) r->l[i] = keep ? t[i] : d[i];
 }
 
-static void fe_sub(const field_t *F, fe *r, const fe *a, const fe *b) {
-    u64 t[4];
-    if (sub4(t, a->l, b->l)) add4(t, t, F->p);
-    memcpy(r->l, t, 32);
+static inline void fe_sub(const field_t *F, fe *r, const fe *a, const fe *b) {
+    u64 t[4], d[4];
+    u64 bw = sub4(t, a->l, b->l);
+    add4(d, t, F->p);
+    for (int i = 0; i < 4; i++) r->l[i] = bw ? d[i] : t[i];
 }
 
-/* Montgomery product a*b/R mod p (CIOS, 64-bit limbs), unrolled; the compiler keeps t[] in registers
- * and emits mulx/adcx-style code with -march=x86-64-v3 (ark-ff's own mul is generated the same way). */
+/* Montgomery product a*b/R mod p, 64-bit limbs, fully unrolled.  Two forms, both standard:
+ *  - fe_mul_nocarry: CIOS without the extra carry word, valid when the modulus' top bit is clear (every field of this
+ *    path; the same shortcut ark-ff's MontBackend takes for such moduli -- dep, from memory): per row
+ *    (A,t0) = t0 + a0*bi; m = t0*ninv; (C,_) = t0 + m*p0; (A,tj) = tj + aj*bi + A; (C,t(j-1)) = tj + m*pj + C; t3 = C + A.
+ *  - fe_mul_general: textbook CIOS with the carry word, any modulus < 2^256.
+ * The compiler keeps t[] in registers and emits mulx/adc code with -march=x86-64-v3. */
 #define MAC(acc, x, y, carry)                                  \
     do {                                                       \
         u128 s__ = (u128)(x) * (y) + (acc) + (carry);          \
         (acc) = (u64)s__;                                      \
         (carry) = (u64)(s__ >> 64);                            \
     } while (0)
-static inline void fe_mul(const field_t *F, fe *r, const fe *a, const fe *b) {
+static inline void fe_mul_general(const field_t *F, fe *r, const fe *a, const fe *b) {
     const u64 p0 = F->p[0], p1 = F->p[1], p2 = F->p[2], p3 = F->p[3], ninv = F->ninv;
     const u64 a0 = a->l[0], a1 = a->l[1], a2 = a->l[2], a3 = a->l[3];
     u64 t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
@@ -112,16 +120,99 @@ static inline void fe_mul(const field_t *F, fe *r, const fe *a, const fe *b) {
     memcpy(r->l, t, 32);
 }
 
+#define NC_ROW(bi)                                                                      \
+    do {                                                                                \
+        u128 s__, q__;                                                                  \
+        u64 A__, C__, m__;                                                              \
+        s__ = (u128)a0 * (bi) + t0;                A__ = (u64)(s__ >> 64);              \
+        m__ = (u64)s__ * ninv;                                                          \
+        q__ = (u128)m__ * p0 + (u64)s__;           C__ = (u64)(q__ >> 64);              \
+        s__ = (u128)a1 * (bi) + t1 + A__;          A__ = (u64)(s__ >> 64);              \
+        q__ = (u128)m__ * p1 + (u64)s__ + C__;     t0 = (u64)q__; C__ = (u64)(q__ >> 64); \
+        s__ = (u128)a2 * (bi) + t2 + A__;          A__ = (u64)(s__ >> 64);              \
+        q__ = (u128)m__ * p2 + (u64)s__ + C__;     t1 = (u64)q__; C__ = (u64)(q__ >> 64); \
+        s__ = (u128)a3 * (bi) + t3 + A__;          A__ = (u64)(s__ >> 64);              \
+        q__ = (u128)m__ * p3 + (u64)s__ + C__;     t2 = (u64)q__; C__ = (u64)(q__ >> 64); \
+        t3 = C__ + A__;                                                                 \
+    } while (0)
+static inline void fe_mul_nocarry(const field_t *F, fe *r, const fe *a, const fe *b) {
+    const u64 p0 = F->p[0], p1 = F->p[1], p2 = F->p[2], p3 = F->p[3], ninv = F->ninv;
+    const u64 a0 = a->l[0], a1 = a->l[1], a2 = a->l[2], a3 = a->l[3];
+    const u64 b0 = b->l[0], b1 = b->l[1], b2 = b->l[2], b3 = b->l[3];
+    u64 t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    NC_ROW(b0); NC_ROW(b1); NC_ROW(b2); NC_ROW(b3);
+    /* result < 2p: one conditional subtraction, branch-free */
+    u64 d0, d1, d2, d3, bw;
+    { u128 d = (u128)t0 - p0;      d0 = (u64)d; bw = (u64)(d >> 64) & 1; }
+    { u128 d = (u128)t1 - p1 - bw; d1 = (u64)d; bw = (u64)(d >> 64) & 1; }
+    { u128 d = (u128)t2 - p2 - bw; d2 = (u64)d; bw = (u64)(d >> 64) & 1; }
+    { u128 d = (u128)t3 - p3 - bw; d3 = (u64)d; bw = (u64)(d >> 64) & 1; }
+    r->l[0] = bw ? t0 : d0; r->l[1] = bw ? t1 : d1; r->l[2] = bw ? t2 : d2; r->l[3] = bw ? t3 : d3;
+}
+static inline void fe_mul(const field_t *F, fe *r, const fe *a, const fe *b) {
+    if (F->nocarry) fe_mul_nocarry(F, r, a, b);
+    else fe_mul_general(F, r, a, b);
+}
+
+/* a^2/R mod p: the six cross products once, doubled, plus the four diagonal squares, then four Montgomery
+ * reduction rows over the 8-limb square (ark-ff's square_in_place has the same shape -- dep, from memory). */
+static inline void fe_sqr(const field_t *F, fe *r, const fe *a) {
+    if (!F->nocarry) { fe_mul_general(F, r, a, a); return; }
+    const u64 p0 = F->p[0], p1 = F->p[1], p2 = F->p[2], p3 = F->p[3], ninv = F->ninv;
+    const u64 a0 = a->l[0], a1 = a->l[1], a2 = a->l[2], a3 = a->l[3];
+    u64 r0, r1, r2, r3, r4, r5, r6, r7, c;
+    u128 s;
+    s = (u128)a0 * a1;            r1 = (u64)s; c = (u64)(s >> 64);
+    s = (u128)a0 * a2 + c;        r2 = (u64)s; c = (u64)(s >> 64);
+    s = (u128)a0 * a3 + c;        r3 = (u64)s; r4 = (u64)(s >> 64);
+    s = (u128)a1 * a2 + r3;       r3 = (u64)s; c = (u64)(s >> 64);
+    s = (u128)a1 * a3 + r4 + c;   r4 = (u64)s; r5 = (u64)(s >> 64);
+    s = (u128)a2 * a3 + r5;       r5 = (u64)s; r6 = (u64)(s >> 64);
+    r7 = r6 >> 63;
+    r6 = (r6 << 1) | (r5 >> 63); r5 = (r5 << 1) | (r4 >> 63); r4 = (r4 << 1) | (r3 >> 63);
+    r3 = (r3 << 1) | (r2 >> 63); r2 = (r2 << 1) | (r1 >> 63); r1 <<= 1;
+    s = (u128)a0 * a0;            r0 = (u64)s; c = (u64)(s >> 64);
+    s = (u128)r1 + c;             r1 = (u64)s; c = (u64)(s >> 64);
+    s = (u128)a1 * a1 + r2 + c;   r2 = (u64)s; c = (u64)(s >> 64);
+    s = (u128)r3 + c;             r3 = (u64)s; c = (u64)(s >> 64);
+    s = (u128)a2 * a2 + r4 + c;   r4 = (u64)s; c = (u64)(s >> 64);
+    s = (u128)r5 + c;             r5 = (u64)s; c = (u64)(s >> 64);
+    s = (u128)a3 * a3 + r6 + c;   r6 = (u64)s; c = (u64)(s >> 64);
+    r7 += c;
+    /* reduction: row i clears limb i; its carry-out joins limb i+4 (running carry `hc` into the next row's top) */
+    u64 m, hc = 0;
+#define SQ_ROW(x0, x1, x2, x3, x4)                                                     \
+    do {                                                                               \
+        m = (x0) * ninv;                                                               \
+        s = (u128)m * p0 + (x0);          c = (u64)(s >> 64);                          \
+        s = (u128)m * p1 + (x1) + c;      (x1) = (u64)s; c = (u64)(s >> 64);           \
+        s = (u128)m * p2 + (x2) + c;      (x2) = (u64)s; c = (u64)(s >> 64);           \
+        s = (u128)m * p3 + (x3) + c;      (x3) = (u64)s; c = (u64)(s >> 64);           \
+        s = (u128)(x4) + c + hc;          (x4) = (u64)s; hc = (u64)(s >> 64);          \
+    } while (0)
+    SQ_ROW(r0, r1, r2, r3, r4);
+    SQ_ROW(r1, r2, r3, r4, r5);
+    SQ_ROW(r2, r3, r4, r5, r6);
+    SQ_ROW(r3, r4, r5, r6, r7);
+#undef SQ_ROW
+    /* a < p < 2^255  =>  (a^2 + M p)/R < 2p < 2^256: hc == 0 here */
+    u64 d0, d1, d2, d3;
+    unsigned long long t;
+    unsigned char bw = _subborrow_u64(0, r4, p0, &t); d0 = t;
+    bw = _subborrow_u64(bw, r5, p1, &t); d1 = t;
+    bw = _subborrow_u64(bw, r6, p2, &t); d2 = t;
+    bw = _subborrow_u64(bw, r7, p3, &t); d3 = t;
+    r->l[0] = bw ? r4 : d0; r->l[1] = bw ? r5 : d1; r->l[2] = bw ? r6 : d2; r->l[3] = bw ? r7 : d3;
+}
+
 /* x^e, left-to-right square-and-multiply over the exponent bits (ark-ff Field::pow, dep). */
 static void fe_pow_u64(const field_t *F, fe *r, const fe *x, u64 e) {
-    fe acc = F->one;
-    int started = 0;
-    for (int i = 63; i >= 0; i--) {
-        if (started) fe_mul(F, &acc, &acc, &acc);
-        if ((e >> i) & 1) {
-            started = 1;
-            fe_mul(F, &acc, &acc, x);
-        }
+    if (e == 0) { *r = F->one; return; }
+    int top = 63 - __builtin_clzll(e);
+    fe acc = *x;                                  /* leading one bit: 1^2 * x */
+    for (int i = top - 1; i >= 0; i--) {
+        fe_sqr(F, &acc, &acc);
+        if ((e >> i) & 1) fe_mul(F, &acc, &acc, x);
     }
     *r = acc;
 }
@@ -143,6 +234,7 @@ static void fe_inv(const field_t *F, fe *r, const fe *x) {
 
 int oref_field_init(field_t *F, const u64 p[4]) {
     memcpy(F->p, p, 32);
+    F->nocarry = (p[3] >> 63) == 0;
     u64 inv = 1;
     for (int i = 0; i < 6; i++) inv *= 2 - p[0] * inv;   /* Newton: p^{-1} mod 2^64 */
     F->ninv = (u64)0 - inv;
@@ -190,35 +282,86 @@ void oref_from_mont(const field_t *F, u64 *out, const u64 *in, size_t n) {
     }
 }
 
+/* element-wise products / squares / sums, for testing the arithmetic itself against Python integers */
+void oref_fe_mul_batch(const field_t *F, u64 *out, const u64 *a, const u64 *b, size_t n) {
+    for (size_t i = 0; i < n; i++) fe_mul(F, (fe *)(out + 4 * i), (const fe *)(a + 4 * i), (const fe *)(b + 4 * i));
+}
+void oref_fe_sqr_batch(const field_t *F, u64 *out, const u64 *a, size_t n) {
+    for (size_t i = 0; i < n; i++) fe_sqr(F, (fe *)(out + 4 * i), (const fe *)(a + 4 * i));
+}
+void oref_fe_addsub_batch(const field_t *F, u64 *sum, u64 *diff, const u64 *a, const u64 *b, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        fe_add(F, (fe *)(sum + 4 * i), (const fe *)(a + 4 * i), (const fe *)(b + 4 * i));
+        fe_sub(F, (fe *)(diff + 4 * i), (const fe *)(a + 4 * i), (const fe *)(b + 4 * i));
+    }
+}
+
 /* ---------------------------------------------------------------- parallel-for */
 
 typedef void (*range_fn)(void *ctx, size_t begin, size_t end);
-typedef struct { range_fn fn; void *ctx; size_t begin, end; } job_t;
 
-static void *job_main(void *arg) {
-    job_t *j = (job_t *)arg;
-    j->fn(j->ctx, j->begin, j->end);
+/* Persistent worker pool (the reference's rayon pool is persistent too): workers sleep on a condition variable
+ * between jobs; a job is a static split of [0, n) into `threads` chunks, the caller runs chunk 0 itself.  One
+ * job at a time (callers serialise on job_mu), one join per call == one rayon barrier per tree level
+ * (R/merkle_tree/mod.rs:458,494). */
+#define POOL_MAX 1024
+static struct {
+    pthread_mutex_t mu, job_mu;
+    pthread_cond_t work, done;
+    pthread_t tid[POOL_MAX];
+    int n_workers;                 /* created so far */
+    unsigned long gen;             /* job generation */
+    range_fn fn; void *ctx; size_t n, chunk; int parts;   /* current job: parts chunks, worker w runs chunk w+1 */
+    int pending;
+} pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER,
+          {0}, 0, 0, NULL, NULL, 0, 0, 0, 0};
+
+static void *pool_main(void *arg) {
+    const int w = (int)(size_t)arg;            /* worker index, runs chunk w + 1 */
+    unsigned long seen = 0;
+    pthread_mutex_lock(&pool.mu);
+    for (;;) {
+        while (pool.gen == seen) pthread_cond_wait(&pool.work, &pool.mu);
+        seen = pool.gen;
+        if (w + 1 < pool.parts) {
+            range_fn fn = pool.fn; void *ctx = pool.ctx;
+            size_t b = (size_t)(w + 1) * pool.chunk, e = b + pool.chunk;
+            if (b > pool.n) b = pool.n;
+            if (e > pool.n) e = pool.n;
+            pthread_mutex_unlock(&pool.mu);
+            fn(ctx, b, e);
+            pthread_mutex_lock(&pool.mu);
+            if (--pool.pending == 0) pthread_cond_signal(&pool.done);
+        }
+    }
     return NULL;
 }
 
-/* One fork/join per call == one rayon barrier per tree level (R/merkle_tree/mod.rs:458,494). */
 static void parallel_for(size_t n, int threads, range_fn fn, void *ctx) {
     if (threads < 1) threads = 1;
+    if (threads > POOL_MAX) threads = POOL_MAX;
     if ((size_t)threads > n) threads = n ? (int)n : 1;
     if (threads == 1) { fn(ctx, 0, n); return; }
-    pthread_t *tid = (pthread_t *)malloc(sizeof(pthread_t) * threads);
-    job_t *jobs = (job_t *)malloc(sizeof(job_t) * threads);
-    size_t chunk = (n + threads - 1) / threads;
-    for (int t = 0; t < threads; t++) {
-        size_t b = (size_t)t * chunk, e = b + chunk;
-        if (b > n) b = n;
-        if (e > n) e = n;
-        jobs[t] = (job_t){fn, ctx, b, e};
-        pthread_create(&tid[t], NULL, job_main, &jobs[t]);
+    pthread_mutex_lock(&pool.job_mu);
+    pthread_mutex_lock(&pool.mu);
+    while (pool.n_workers < threads - 1) {
+        /* a new worker must not mistake the job about to be posted for an old one: it starts with seen = 0 and
+         * gen >= 1 only after the post below, so it simply picks this job up */
+        if (pthread_create(&pool.tid[pool.n_workers], NULL, pool_main, (void *)(size_t)pool.n_workers)) break;
+        pthread_detach(pool.tid[pool.n_workers]);
+        pool.n_workers++;
     }
-    for (int t = 0; t < threads; t++) pthread_join(tid[t], NULL);
-    free(tid);
-    free(jobs);
+    int parts = pool.n_workers + 1 < threads ? pool.n_workers + 1 : threads;
+    size_t chunk = (n + parts - 1) / parts;
+    pool.fn = fn; pool.ctx = ctx; pool.n = n; pool.chunk = chunk; pool.parts = parts; pool.pending = parts - 1;
+    pool.gen++;
+    pthread_cond_broadcast(&pool.work);
+    pthread_mutex_unlock(&pool.mu);
+    fn(ctx, 0, chunk < n ? chunk : n);
+    pthread_mutex_lock(&pool.mu);
+    while (pool.pending > 0) pthread_cond_wait(&pool.done, &pool.mu);
+    pthread_mutex_unlock(&pool.mu);
+    pthread_mutex_unlock(&pool.job_mu);
 }
 
 /* ---------------------------------------------------------------- Poseidon */

@@ -109,3 +109,30 @@ def test_multiproof_prefix_lengths_kat():
     _, prefix, suffixes, idx = T.generate_multi_proof(range(8))
     assert prefix == K["multiproof_prefix_lengths_8_leaves"]["value"]     # R/merkle_tree/tests/mod.rs:166
     assert all(p + len(s) == 2 for p, s in zip(prefix, suffixes))
+
+
+@pytest.mark.parametrize("fname", ["BLS12_381_FR", "BN254_FR", "JUBJUB_FR", "BLS12_377_FR"])
+def test_c_field_routines_on_pattern_limbs(fname):
+    """The C oracle's unrolled Montgomery product, dedicated squaring and branch-free add/sub against Python integers on
+    operands whose 64-bit limbs are drawn from {0, 1, 2^64-1, 2^63, 2^32-1, random}: every carry position is hit."""
+    p = getattr(OF, fname)
+    rng = np.random.default_rng(7)
+    pat = np.array([0, 1, (1 << 64) - 1, 1 << 63, (1 << 32) - 1, (1 << 64) - 2], dtype=np.uint64)
+    n = 20000
+    def draw():
+        choice = rng.integers(0, 9, size=(n, 4))
+        rnd = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+        limbs = np.where(choice < 6, pat[np.minimum(choice, 5)], rnd)
+        vals = [OF.from_limbs([int(x) for x in row]) % p for row in limbs]
+        vals[0], vals[1], vals[2] = p - 1, 0, p - 2
+        return vals
+    A, B = draw(), draw()
+    a = np.array([OF.to_limbs(v) for v in A], dtype=np.uint64)
+    b = np.array([OF.to_limbs(v) for v in B], dtype=np.uint64)
+    mul, sqr, add, sub = cref.field_ops(p, a, b)
+    rinv = pow(1 << 256, -1, p)
+    for i in range(n):
+        assert OF.from_limbs([int(x) for x in mul[i]]) == A[i] * B[i] * rinv % p
+        assert OF.from_limbs([int(x) for x in sqr[i]]) == A[i] * A[i] * rinv % p
+        assert OF.from_limbs([int(x) for x in add[i]]) == (A[i] + B[i]) % p
+        assert OF.from_limbs([int(x) for x in sub[i]]) == (A[i] - B[i]) % p
