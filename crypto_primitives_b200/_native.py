@@ -22,11 +22,16 @@ SIGNATURES = {
     "cpb_abi_version": (C.c_int, []),
     "cpb_version": (C.c_int, []),
     "cpb_device_count": (C.c_int, []),
+    "cpb_host_register": (C.c_int, [vp, C.c_size_t]),
+    "cpb_host_unregister": (C.c_int, [vp]),
+    "cpb_merkle_poseidon_launch_count": (C.c_size_t, [C.c_size_t]),
     "cpb_field_modulus": (C.c_int, [C.c_int, u64p]),
     "cpb_field_to_montgomery": (C.c_int, [C.c_int, C.c_int, u64p, u64p, C.c_size_t]),
     "cpb_field_from_montgomery": (C.c_int, [C.c_int, C.c_int, u64p, u64p, C.c_size_t]),
+    "cpb_field_to_montgomery_dev": (C.c_int, [C.c_int, C.c_int, vp, vp, C.c_size_t, vp]),
+    "cpb_field_from_montgomery_dev": (C.c_int, [C.c_int, C.c_int, vp, vp, C.c_size_t, vp]),
     "cpb_poseidon_find_ark_and_mds": (C.c_int, [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, u64p, u64p]),
-    "cpb_poseidon_default_entry": (C.c_int, [C.c_int, C.c_int, u64p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cpb_poseidon_default_entry": (C.c_int, [C.c_int, C.c_int, C.c_int, u64p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cpb_poseidon_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, u64p, u64p, C.c_int, C.POINTER(vp)]),
     "cpb_poseidon_ctx_destroy": (None, [vp]),
     "cpb_poseidon_ctx_is_sparse": (C.c_int, [vp]),

@@ -483,12 +483,14 @@ bool curve_info(int curve_id, CurveInfo& ci) {
 
 template <class K> cpb_status ped_grid(K kernel, size_t smem, int sms, long n, int& grid) {
     static thread_local const void* last = nullptr;
-    static thread_local int occ = 0;
-    if (last != (const void*)kernel) {
+    static thread_local int occ = 0, last_dev = -1;          // the attribute and the occupancy belong to (kernel, device)
+    int dev = -1;
+    CPB_CUDA(cudaGetDevice(&dev));
+    if (last != (const void*)kernel || last_dev != dev) {
         CPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kPedBlock, smem));
         if (occ < 1) return fail(CPB_CUDA_ERROR, "pedersen kernel does not fit on an SM");
-        last = (const void*)kernel;
+        last = (const void*)kernel; last_dev = dev;
     }
     long need = (n + kPedBlock - 1) / kPedBlock, cap = (long)sms * occ;
     grid = (int)(need < cap ? need : cap);

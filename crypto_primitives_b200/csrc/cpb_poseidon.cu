@@ -290,6 +290,35 @@ int cpb_device_count(void) {
     return ok;
 }
 
+// Kernel launches one cpb_merkle_poseidon_build_dev over n leaves issues (leaf hash included): what bench.py reports as
+// gpu_launches.  Mirrors merkle_build_streams below.
+size_t cpb_merkle_poseidon_launch_count(size_t n) {
+    if (!pow2_gt1(n)) return 0;
+    int h = 0;
+    while (((size_t)1 << h) < n) h++;
+    size_t S = merkle_streams(n);
+    int lg = 0;
+    while (((size_t)1 << lg) < S) lg++;
+    return S > 1 ? S * (size_t)(1 + (h - lg)) + (size_t)lg : (size_t)(1 + h);
+}
+
+// Page-lock a caller-owned host buffer so that the host-pointer entry points copy at full PCIe rate and overlap with
+// hashing (a Rust Vec<Fr> is pageable; the shim can pin it once and reuse it).  cudaHostRegister / cudaHostUnregister.
+cpb_status cpb_host_register(void* ptr, size_t bytes) {
+    return cpb::guarded([&]() -> cpb_status {
+    if (!ptr || !bytes) return fail(CPB_NULL_POINTER, "null buffer");
+    CPB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return CPB_OK;
+    });
+}
+cpb_status cpb_host_unregister(void* ptr) {
+    return cpb::guarded([&]() -> cpb_status {
+    if (!ptr) return fail(CPB_NULL_POINTER, "null buffer");
+    CPB_CUDA(cudaHostUnregister(ptr));
+    return CPB_OK;
+    });
+}
+
 cpb_status cpb_field_modulus(int field_id, uint64_t out[4]) {
     return cpb::guarded([&]() -> cpb_status {
     const uint64_t* m = host::field_modulus(field_id);
@@ -324,6 +353,36 @@ static cpb_status field_convert(int field_id, int device, const uint64_t* in, ui
     if (e != cudaSuccess) return fail(CPB_CUDA_ERROR, "field conversion failed: %s", cudaGetErrorString(e));
     return CPB_OK;
 }
+static cpb_status field_convert_dev(int field_id, int device, const uint64_t* in, uint64_t* out, size_t n, int to_mont, void* stream) {
+    if (!host::field_modulus(field_id)) return fail(CPB_BAD_PARAMS, "unknown field id %d", field_id);
+    if (n == 0) return CPB_OK;
+    if (!in || !out) return fail(CPB_NULL_POINTER, "null buffer");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(CPB_NO_DEVICE, "cudaSetDevice(%d) failed", device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const u32* d_in = (const u32*)in;
+    u32* d_out = (u32*)out;
+    long left = (long)n, off = 0;
+    while (left > 0) {                                  // grid.x limit is not an issue (2^31-1), but keep launches bounded
+        long m = left < (1L << 28) ? left : (1L << 28);
+        int grid = (int)((m + 127) / 128);
+        switch (field_id) {
+            case 0: k_field_convert<Bls12_381_Fr><<<grid, 128, 0, st>>>(d_in + 8 * off, d_out + 8 * off, m, to_mont); break;
+            case 1: k_field_convert<Bn254_Fr><<<grid, 128, 0, st>>>(d_in + 8 * off, d_out + 8 * off, m, to_mont); break;
+            case 2: k_field_convert<Jubjub_Fr><<<grid, 128, 0, st>>>(d_in + 8 * off, d_out + 8 * off, m, to_mont); break;
+            case 3: k_field_convert<Bls12_377_Fr><<<grid, 128, 0, st>>>(d_in + 8 * off, d_out + 8 * off, m, to_mont); break;
+        }
+        CPB_CUDA(cudaGetLastError());
+        left -= m; off += m;
+    }
+    return CPB_OK;
+}
+cpb_status cpb_field_to_montgomery_dev(int field_id, int device, const uint64_t* in, uint64_t* out, size_t n, void* stream) {
+    return cpb::guarded([&]() -> cpb_status { return field_convert_dev(field_id, device, in, out, n, 1, stream); });
+}
+cpb_status cpb_field_from_montgomery_dev(int field_id, int device, const uint64_t* in, uint64_t* out, size_t n, void* stream) {
+    return cpb::guarded([&]() -> cpb_status { return field_convert_dev(field_id, device, in, out, n, 0, stream); });
+}
 cpb_status cpb_field_to_montgomery(int field_id, int device, const uint64_t* in, uint64_t* out, size_t n) {
     return cpb::guarded([&]() -> cpb_status {
     return field_convert(field_id, device, in, out, n, 1);
@@ -355,12 +414,12 @@ cpb_status cpb_poseidon_find_ark_and_mds(int field_id, uint64_t prime_bits, int 
     });
 }
 
-cpb_status cpb_poseidon_default_entry(int rate, int optimized_for_weights, uint64_t* alpha, int* full_rounds,
+cpb_status cpb_poseidon_default_entry(int field_id, int rate, int optimized_for_weights, uint64_t* alpha, int* full_rounds,
                                       int* partial_rounds, int* skip_matrices) {
     return cpb::guarded([&]() -> cpb_status {
     host::DefaultEntry e;
-    if (!host::default_entry(rate, optimized_for_weights != 0, e))
-        return fail(CPB_BAD_PARAMS, "no default entry for rate %d", rate);   // reference returns None
+    if (!host::default_entry(field_id, rate, optimized_for_weights != 0, e))
+        return fail(CPB_BAD_PARAMS, "no default entry for field %d rate %d", field_id, rate);   // reference returns None / has no impl
     if (alpha) *alpha = e.alpha;
     if (full_rounds) *full_rounds = e.rf;
     if (partial_rounds) *partial_rounds = e.rp;
@@ -379,7 +438,7 @@ cpb_status cpb_poseidon_ctx_create(int field_id, int rate, int capacity, int ful
     if (!mod) return fail(CPB_BAD_PARAMS, "unknown field id %d", field_id);
     if (!ark || !mds) return fail(CPB_NULL_POINTER, "null ark/mds");
     if (rate < 1 || capacity < 1 || rate + capacity > 16 || full_rounds < 0 || partial_rounds < 0 ||
-        full_rounds + partial_rounds < 1 || (full_rounds & 1))
+        full_rounds + partial_rounds < 1)
         return fail(CPB_BAD_PARAMS, "bad Poseidon shape rate=%d capacity=%d RF=%d RP=%d", rate, capacity, full_rounds,
                     partial_rounds);
     host::Field F(mod);

@@ -90,8 +90,9 @@ template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const Po
     for (int i = 0; i < T; i++) fp_zero(n[i]);
 #pragma unroll 1
     for (int phase = 0; phase < 2; phase++) {
+        const int cnt = phase == 0 ? half : P.rf - half;   // odd RF: floor(RF/2) rounds before, ceil(RF/2) after (mod.rs:98-121)
 #pragma unroll 1
-        for (int q = 0; q < half; q++) {
+        for (int q = 0; q < cnt; q++) {
             pos_add_vec<F, T>(s, cs + 8 * (P.off_c + (phase * half + q) * T));
 #pragma unroll 1
             for (int j = 0; j < T; j++) {

@@ -108,7 +108,8 @@ inline void find_poseidon_ark_and_mds(const Field& F, u64 prime_bits, int rate, 
 // Default-parameter entry tables of the reference's BLS12-381 test field (R/sponge/test.rs:13-32):
 // (rate, alpha, full, partial, skip).  Other fields carry no table in the reference.
 struct DefaultEntry { int rate; u64 alpha; int rf, rp, skip; };
-inline bool default_entry(int rate, bool optimized_for_weights, DefaultEntry& e) {
+inline bool default_entry(int field_id, int rate, bool optimized_for_weights, DefaultEntry& e) {
+    if (field_id != 0) return false;   // PoseidonDefaultConfig is implemented per field; the reference does so for its BLS12-381 Fr test field only
     static const DefaultEntry C[7] = {{2, 17, 8, 31, 0}, {3, 5, 8, 56, 0}, {4, 5, 8, 56, 0}, {5, 5, 8, 57, 0},
                                       {6, 5, 8, 57, 0},  {7, 5, 8, 57, 0}, {8, 5, 8, 57, 0}};
     if (rate < 2 || rate > 8) return false;

@@ -73,17 +73,28 @@ struct cpb_poseidon_ctx {
 
 namespace cpb {
 
-template <class K> cpb_status grid_for(K kernel, size_t smem, int sms, long n, int& grid) {
+// cudaFuncAttributeMaxDynamicSharedMemorySize and the occupancy are properties of (kernel, device): the cache key holds the
+// current device, so one host thread driving contexts on several GPUs re-configures the kernel on each of them.
+template <class K> cpb_status configure_kernel(K kernel, size_t smem, int block, int& occ_out) {
     static thread_local const void* last = nullptr;
-    static thread_local int last_occ = 0;
+    static thread_local int last_occ = 0, last_dev = -1;
     static thread_local size_t last_smem = 0;
-    if (last != (const void*)kernel || last_smem != smem) {
+    int dev = -1;
+    CPB_CUDA(cudaGetDevice(&dev));
+    if (last != (const void*)kernel || last_smem != smem || last_dev != dev) {
         if (smem > 48 * 1024) CPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
-        CPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, smem));
+        CPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem));
         if (occ < 1) return fail(CPB_CUDA_ERROR, "kernel does not fit on an SM (smem=%zu)", smem);
-        last = (const void*)kernel; last_occ = occ; last_smem = smem;
+        last = (const void*)kernel; last_occ = occ; last_smem = smem; last_dev = dev;
     }
+    occ_out = last_occ;
+    return CPB_OK;
+}
+
+template <class K> cpb_status grid_for(K kernel, size_t smem, int sms, long n, int& grid) {
+    int last_occ = 0;
+    CPB_TRY(configure_kernel(kernel, smem, kBlock, last_occ));
     // One CTA per 128 hashes (capped; the kernels grid-stride).  Short-lived CTAs instead of one persistent
     // wave let the block scheduler interleave kernels from different streams: the latency-bound top
     // levels of one Merkle subtree then overlap with the bulk hashing of the next (merkle build).
@@ -187,11 +198,8 @@ k_poseidon_compress_team(PoseidonDev P, const u32* __restrict__ consts, const u3
 template <class F>
 cpb_status launch_team_f(cpb_poseidon_ctx* c, const u32* pairs, u32* out, size_t n, cudaStream_t st) {
     size_t smem = (size_t)c->dev.n_elems * 32 + (size_t)kTeamXbWords * 4;
-    static thread_local const void* configured = nullptr;
-    if (smem > 48 * 1024 && configured != (const void*)k_poseidon_compress_team<F>) {
-        CPB_CUDA(cudaFuncSetAttribute(k_poseidon_compress_team<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = (const void*)k_poseidon_compress_team<F>;
-    }
+    int occ = 0;
+    CPB_TRY(configure_kernel(k_poseidon_compress_team<F>, smem, 96, occ));
     long nblk = ((long)n + 31) / 32;
     k_poseidon_compress_team<F><<<(int)nblk, 96, smem, st>>>(c->dev, c->d_consts, pairs, out, (long)n);
     CPB_CUDA(cudaGetLastError());

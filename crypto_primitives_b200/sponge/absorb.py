@@ -123,6 +123,9 @@ def _ints(x, field: Field) -> list:
     if isinstance(x, WithLength):
         return _ints(usize(_len(x.item)), field) + _ints(x.item, field)
     if isinstance(x, (list, tuple)):
+        if len(x) and all(isinstance(i, UInt) and i.bits == 8 for i in x):
+            # &[u8] / Vec<u8> take the u8 batch specialisation (absorb.rs:137-141): length prefix + packed chunks
+            return _ints(bytes(i.value % 256 for i in x), field)
         out = []
         for i in x:
             out += _ints(i, field)

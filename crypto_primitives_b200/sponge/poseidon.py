@@ -86,12 +86,14 @@ def find_poseidon_ark_and_mds(field: Field, prime_bits: int, rate: int, full_rou
 
 
 def get_default_poseidon_parameters(field: Field, rate: int, optimized_for_weights: bool):
-    """PoseidonDefaultConfigField::get_default_poseidon_parameters (traits.rs:59-103).  The entry
-    tables are those of the reference's BLS12-381 Fr test field (R/sponge/test.rs:13-32); as in the
-    reference, a rate without an entry yields None."""
+    """PoseidonDefaultConfigField::get_default_poseidon_parameters (traits.rs:59-103).  The entry tables are per field
+    (`PoseidonDefaultConfig`); the reference implements them for its BLS12-381 Fr test field only
+    (R/sponge/test.rs:13-32).  As in the reference, a rate without an entry yields None; so does a field without a table
+    (there the reference would not compile) -- derive parameters for other fields explicitly with
+    find_poseidon_ark_and_mds and a round count / alpha chosen for that field."""
     alpha = C.c_uint64()
     rf, rp, skip = C.c_int(), C.c_int(), C.c_int()
-    st = N.lib.cpb_poseidon_default_entry(rate, int(bool(optimized_for_weights)), C.byref(alpha), C.byref(rf), C.byref(rp), C.byref(skip))
+    st = N.lib.cpb_poseidon_default_entry(field.id, rate, int(bool(optimized_for_weights)), C.byref(alpha), C.byref(rf), C.byref(rp), C.byref(skip))
     if st != N.CPB_OK:
         return None
     ark, mds = find_poseidon_ark_and_mds(field, field.modulus_bit_size, rate, rf.value, rp.value, skip.value)
@@ -230,10 +232,13 @@ class PoseidonSponge:
         native = self.parameters.field
         field = native if field is None else field
         sizes = list(sizes)
+        # native field: an empty `sizes` is "all Full" and still goes through squeeze_native_field_elements(0), which
+        # permutes from Absorbing mode and switches to Squeezing{0} (mod.rs:291-307, R/sponge/mod.rs:164-179, mod.rs:323-345);
+        # only the non-native default implementation returns early (R/sponge/mod.rs:61-63)
+        if field.modulus == native.modulus and all(s == FULL for s in sizes):
+            return self.squeeze_native_field_elements(len(sizes)).reshape(-1, 4)
         if not sizes:
             return np.zeros((0, 4), dtype=np.uint64)
-        if field.modulus == native.modulus and all(s == FULL for s in sizes):
-            return self.squeeze_native_field_elements(len(sizes))
         widths = []
         for s in sizes:
             if s == FULL:

@@ -73,12 +73,17 @@ typedef struct cpb_bowe_hopwood_ctx cpb_bowe_hopwood_ctx;
 
 const char* cpb_last_error(void);
 
-/* ABI revision of this header: bumped when entry points or status codes are added (2 = CPB_INTERNAL_ERROR, cpb_abi_version). */
-#define CPB_ABI_VERSION 2
+/* ABI revision of this header: bumped when entry points or status codes are added (2 = CPB_INTERNAL_ERROR, cpb_abi_version; 3 = _dev field conversion, host pinning, launch count, multi-GPU build, CPB_NCCL_ERROR). */
+#define CPB_ABI_VERSION 3
 int cpb_abi_version(void);
 int cpb_version(void);
 /* Number of visible CUDA devices with compute capability 10.x (0 when none / no driver). */
 int cpb_device_count(void);
+
+/* Page-lock / unlock a caller-owned host buffer (cudaHostRegister, portable): host-pointer entry points then copy at
+ * full PCIe rate and overlap copies with hashing.  A Rust `Vec<Fr>` is pageable; the shim may pin it once and reuse it. */
+cpb_status cpb_host_register(void* ptr, size_t bytes);
+cpb_status cpb_host_unregister(void* ptr);
 
 /* ---- fields ----------------------------------------------------------------------------- */
 /* Modulus as 4 LE limbs.  (ark-ff `F::MODULUS`.) */
@@ -87,6 +92,9 @@ cpb_status cpb_field_modulus(int field_id, uint64_t out[4]);
  * Convenience for non-Rust callers; ark-ff callers already hold Montgomery limbs. */
 cpb_status cpb_field_to_montgomery(int field_id, int device, const uint64_t* in, uint64_t* out, size_t n);
 cpb_status cpb_field_from_montgomery(int field_id, int device, const uint64_t* in, uint64_t* out, size_t n);
+/* Same on device buffers (in-place allowed: out == in), asynchronous on `stream`. */
+cpb_status cpb_field_to_montgomery_dev(int field_id, int device, const uint64_t* in, uint64_t* out, size_t n, void* stream);
+cpb_status cpb_field_from_montgomery_dev(int field_id, int device, const uint64_t* in, uint64_t* out, size_t n, void* stream);
 
 /* ---- Poseidon --------------------------------------------------------------------------- */
 /* find_poseidon_ark_and_mds, R/sponge/poseidon/traits.rs:105-146 (Grain LFSR of
@@ -95,10 +103,12 @@ cpb_status cpb_field_from_montgomery(int field_id, int device, const uint64_t* i
 cpb_status cpb_poseidon_find_ark_and_mds(int field_id, uint64_t prime_bits, int rate, int full_rounds,
                                          int partial_rounds, int skip_matrices, uint64_t* ark_out,
                                          uint64_t* mds_out);
-/* PoseidonDefaultConfigField::get_default_poseidon_parameters, traits.rs:59-103, with the entry
- * tables of R/sponge/test.rs:13-32 (rate 2..8, capacity 1).  Writes the shape; a second call of
+/* PoseidonDefaultConfigField::get_default_poseidon_parameters, traits.rs:59-103.  The entry tables belong to a field
+ * (`impl PoseidonDefaultConfig<N> for FrConfig`): the reference has them for its BLS12-381 Fr test field only
+ * (R/sponge/test.rs:13-32, rate 2..8, capacity 1); any other field, or a rate without an entry, -> CPB_BAD_PARAMS (the
+ * tables' alpha = 5 is not even a permutation of BLS12-377 Fr).  Writes the shape; a second call of
  * cpb_poseidon_find_ark_and_mds with that shape yields ark/mds. */
-cpb_status cpb_poseidon_default_entry(int rate, int optimized_for_weights, uint64_t* alpha, int* full_rounds,
+cpb_status cpb_poseidon_default_entry(int field_id, int rate, int optimized_for_weights, uint64_t* alpha, int* full_rounds,
                                       int* partial_rounds, int* skip_matrices);
 
 /* PoseidonConfig::new, R/sponge/poseidon/mod.rs:189-217.  ark: (full+partial) x t, mds: t x t
@@ -145,6 +155,8 @@ cpb_status cpb_merkle_poseidon_build(cpb_poseidon_ctx* leaf_ctx, cpb_poseidon_ct
 cpb_status cpb_merkle_poseidon_build_dev(cpb_poseidon_ctx* leaf_ctx, cpb_poseidon_ctx* node_ctx,
                                          const uint64_t* leaves, size_t leaf_len, size_t n, uint64_t* leaf_nodes,
                                          uint64_t* non_leaf_nodes, void* stream);
+/* Number of kernel launches one cpb_merkle_poseidon_build_dev over n leaves issues (0 when n is not a power of two > 1). */
+size_t cpb_merkle_poseidon_launch_count(size_t n);
 /* MerkleTree::new_with_leaf_digest (mod.rs:424-523): inner levels only. */
 cpb_status cpb_merkle_poseidon_from_digests(cpb_poseidon_ctx* node_ctx, const uint64_t* leaf_digests, size_t n,
                                             uint64_t* non_leaf_nodes);

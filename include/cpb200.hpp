@@ -55,7 +55,7 @@ public:
     // PoseidonDefaultConfigField::get_default_poseidon_parameters (traits.rs:59-103); nullptr where the reference returns None.
     static std::unique_ptr<Config> get_default_poseidon_parameters(int field, int rate, bool optimized_for_weights, int device = 0) {
         uint64_t alpha; int rf, rp, skip;
-        if (cpb_poseidon_default_entry(rate, optimized_for_weights, &alpha, &rf, &rp, &skip) != CPB_OK) return nullptr;
+        if (cpb_poseidon_default_entry(field, rate, optimized_for_weights, &alpha, &rf, &rp, &skip) != CPB_OK) return nullptr;
         uint64_t mod[4];
         check(cpb_field_modulus(field, mod));
         uint64_t bits = 256;

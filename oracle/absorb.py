@@ -151,10 +151,10 @@ def squeeze_field_elements_with_sizes(sponge, sizes, p2: int | None = None) -> l
     """mod.rs:291-307 over R/sponge/mod.rs:57-96, 170-187: native and all Full -> native squeeze; otherwise bits."""
     p = sponge.cfg.p
     p2 = p if p2 is None else p2
-    if not sizes:
-        return []
-    if p2 == p and all(s == FULL for s in sizes):
+    if p2 == p and all(s == FULL for s in sizes):       # incl. empty `sizes`: permutes and enters Squeezing{0} (mod.rs:323-345)
         return sponge.squeeze_native_field_elements(len(sizes))
+    if not sizes:                                       # non-native default implementation only (R/sponge/mod.rs:61-63)
+        return []
     widths = [num_bits(s, p2) for s in sizes]
     bits = squeeze_bits(sponge, sum(widths))
     out, pos = [], 0

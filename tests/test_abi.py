@@ -47,6 +47,10 @@ def test_default_parameters_match_reference_kats():
             assert cfg.capacity == 1 and cfg.rate == rate
     assert cp.get_default_poseidon_parameters(f, 9, False) is None          # traits.rs:102 -> None
     assert cp.get_default_poseidon_parameters(f, 1, False) is None
+    # the tables belong to BLS12-381 Fr (R/sponge/test.rs:13-32); no other field has an impl in the reference
+    for other in (cp.BN254_FR, cp.JUBJUB_FR, cp.BLS12_377_FR):
+        assert cp.get_default_poseidon_parameters(other, 2, False) is None
+        assert cp.get_default_poseidon_parameters(other, 3, True) is None
 
 
 def test_find_ark_and_mds_rejects_wrong_bit_size():

@@ -204,6 +204,10 @@ def test_sponge_interface_surface_matches_oracle():
     assert f.to_ints(gf.squeeze_field_elements_with_sizes(sizes)) == OA.squeeze_field_elements_with_sizes(of, [10, OA.FULL, 128, 1, 255])
     assert gf.squeeze_bits(300) == OA.squeeze_bits(of, 300)
     assert gf.squeeze_bytes(77) == OA.squeeze_bytes(of, 77)
+    # empty native squeeze: permutes, Squeezing{0} (mod.rs:291-307 -> :323-345)
+    ge, oe = g.fork(b"e"), OA.fork(o, b"e")
+    assert ge.squeeze_field_elements_with_sizes([]).shape == (0, 4) and OA.squeeze_field_elements_with_sizes(oe, []) == []
+    assert ge.mode == ("Squeezing", 0) and f.to_ints(ge.squeeze_native_field_elements(2)) == oe.squeeze_native_field_elements(2)
     # into another field (BN254 Fr): Full = 253 bits of the bit stream
     bn = cp.BN254_FR
     assert bn.to_ints(gf.squeeze_field_elements(3, bn)) == OA.squeeze_field_elements_with_sizes(of, [OA.FULL] * 3, bn.modulus)

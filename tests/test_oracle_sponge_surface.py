@@ -72,6 +72,17 @@ def test_squeeze_cast_native_and_sizes():
         pos += w
     with pytest.raises(ValueError):
         OA.squeeze_field_elements_with_sizes(s3, [256])
+    # an empty native squeeze still permutes and enters Squeezing{0} (mod.rs:291-307 -> :323-345): the transcript moves on
+    s5, _ = sponge("bls_sponge_fixture")
+    absorb(s5, OA.Fe(7, cfg.p))
+    s6 = copy.deepcopy(s5)
+    assert OA.squeeze_field_elements_with_sizes(s5, []) == [] and s5.mode == ("S", 0)
+    s6._permute()
+    assert s5.state == s6.state
+    # the non-native default implementation returns early without touching the sponge (R/sponge/mod.rs:61-63)
+    s7 = copy.deepcopy(s6)
+    from oracle import fields as OF
+    assert OA.squeeze_field_elements_with_sizes(s7, [], OF.BN254_FR) == [] and s7.state == s6.state and s7.mode == s6.mode
 
 
 def test_macros_shape():

@@ -179,3 +179,26 @@ def test_crafted_sbox_operands(shim, which):
     for sp in (1, 0):
         _, out = run(shim, FID[fname], cfg, inp, sp)
         assert (out == exp).all()
+
+
+def test_odd_full_rounds(shim):
+    """PoseidonConfig::new asserts shapes only (R/sponge/poseidon/mod.rs:189-217) and permute runs floor(RF/2) full rounds
+    before and ceil(RF/2) after the partial ones (:98-121): odd RF must be accepted and match, sparse and dense, in the
+    one-hash-per-thread code and in the three-warp team model."""
+    rnd = random.Random(11)
+    for p, fid in ((OF.BLS12_381_FR, 0), (OF.BN254_FR, 1)):
+        for rf, rp, alpha in ((1, 0, 5), (1, 3, 5), (3, 4, 17), (5, 6, 5), (7, 2, 3), (3, 0, 5)):
+            t = 3
+            ark = [[rnd.randrange(p) for _ in range(t)] for _ in range(rf + rp)]
+            mds = [[rnd.randrange(p) for _ in range(t)] for _ in range(t)]
+            cfg = OP.PoseidonConfig(p, rf, rp, alpha, ark, mds, 2, 1)
+            check(shim, fid, cfg, Ls=(0, 2, 3), n=4, expect_sparse=1 if (rp > 0 and rf >= 3) else 0)
+            arkm = cref.ints_to_mont([x for r in ark for x in r], p)
+            mdsm = cref.ints_to_mont([x for r in mds for x in r], p)
+            pairs = synth_elems(5 + rf, (33, 2), p)
+            exp = cref.Poseidon(cfg).compress_batch(pairs)
+            for sp in (1, 0):
+                out = np.zeros((33, 4), dtype=np.uint64)
+                rc = shim.host_poseidon_team_compress(fid, rf, rp, C.c_ulonglong(alpha), _P(arkm), _P(mdsm), sp,
+                                                      _P(np.ascontiguousarray(pairs)), C.c_long(33), _P(out))
+                assert rc >= 0 and np.array_equal(out, exp), (rf, rp, sp)
