@@ -148,10 +148,10 @@ def wide_madds_per_perm(field_key: str, t: int, rf: int, rp: int, alpha: int) ->
     return rf * (t * sbox + t * dot) + rp * (sbox + dot + (t - 1) * mul)
 
 
-def merkle_launches(n: int) -> int:
+def merkle_launches(ctx, n: int) -> int:
     """Kernel launches of one cpb_merkle_poseidon_build_dev over n leaves (csrc/cpb_poseidon.cu: merkle_build_streams)."""
     from crypto_primitives_b200 import _native as N
-    return int(N.lib.cpb_merkle_poseidon_launch_count(n))
+    return int(N.lib.cpb_merkle_poseidon_launch_count(ctx, n))
 
 
 # --------------------------------------------------------------------------------- CPU arm (oracle/cref)
@@ -256,7 +256,7 @@ def run_b200(args):
     import torch.distributed as dist
     import crypto_primitives_b200 as cp
     from crypto_primitives_b200 import _native as N
-    from crypto_primitives_b200.distributed import CudaMixedBackend, CudaPoseidonBackend, level_slices, sharded_merkle_build
+    from crypto_primitives_b200.distributed import CudaMixedBackend, CudaPoseidonBackend, Exchange, level_slices, sharded_merkle_build
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -276,6 +276,10 @@ def run_b200(args):
     params = poseidon_params(cp, field_key)
     fid = params.field.id
     backend = CudaPoseidonBackend(params, params, local_rank)
+    # N > 1: the subtree roots are exchanged inside the last kernel of each rank's build over NVLink peer memory (CUDA IPC);
+    # CPB_BENCH_EXCHANGE=nccl selects the torch.distributed all-gather for the headline instead (timed alongside anyway)
+    use_fused = world > 1 and os.environ.get("CPB_BENCH_EXCHANGE", "fused") != "nccl"
+    ex = Exchange(local_rank) if world > 1 else None
     # this rank's slice of the global leaf stream: leaves [rank*n_local, (rank+1)*n_local)
     leaves = BI.field_elements_torch(torch, N, fid, seed, rank * n_local * leaf_len, n_local * leaf_len, local_rank).view(n_local, leaf_len, 4)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
@@ -292,8 +296,8 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return bool(t.item())
 
-    def step():
-        return sharded_merkle_build(backend, leaves, gather="roots")
+    def step(fused=use_fused):
+        return sharded_merkle_build(backend, leaves, gather="roots", exchange=ex if fused else None)
 
     perms_total = 2 * n_total - 1
     for _ in range(args.warmup):
@@ -324,6 +328,27 @@ def run_b200(args):
     ms_per_step = total_ms / args.steps
     value = perms_total / (ms_per_step * 1e-3)
 
+    # ---- N > 1: the other root exchange (NCCL all-gather issued from Python <-> fused peer-memory kernel), 3 steps
+    other_ms = None
+    if world > 1:
+        ts = []
+        for i in range(4):
+            flush.zero_()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step(fused=not use_fused)
+            e1.record()
+            torch.cuda.synchronize()
+            if i:
+                ts.append(e0.elapsed_time(e1))
+        tt = torch.tensor([sum(ts) / len(ts)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        other_ms = float(tt.item())
+        tree = step()
+        torch.cuda.synchronize()
+        root = tree.root.clone()
+
     # ---- parity of the timed result: the root against the oracle's committed root (every rank holds the root)
     g = gold.get(args.workload, {})
     root_u = u64_list(root.cpu())
@@ -349,15 +374,16 @@ def run_b200(args):
     h_leaves.copy_(leaves)
     h_leaf_nodes = torch.empty((n_local, 4), dtype=torch.int64, pin_memory=True)
     h_nodes = torch.empty((max(n_local - 1, 1), 4), dtype=torch.int64, pin_memory=True)
+    h_top = torch.empty((max(world - 1, 1), 4), dtype=torch.int64, pin_memory=True)
 
     def e2e_call(hl, hln, hn):
+        if world > 1:       # this rank's shard through the host-pointer sharded call: copies, hashing, root exchange, top levels
+            N.check(N.lib.cpb_merkle_poseidon_build_sharded(ctx, ctx, ex.handle, N.C.cast(hl.data_ptr(), N.u64p), leaf_len, n_local,
+                                                            N.C.cast(hln.data_ptr(), N.u64p), N.C.cast(hn.data_ptr(), N.u64p),
+                                                            N.C.cast(h_top.data_ptr(), N.u64p)))
+            return h_top[0]
         N.check(N.lib.cpb_merkle_poseidon_build(ctx, ctx, N.C.cast(hl.data_ptr(), N.u64p), leaf_len, n_local,
                                                 N.C.cast(hln.data_ptr(), N.u64p), N.C.cast(hn.data_ptr(), N.u64p)))
-        if world > 1:
-            r = hn[0].to(dev, non_blocking=False).reshape(1, 4)
-            roots = torch.empty((world, 4), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(roots, r)
-            return backend.from_digests(roots)[0].cpu()
         return hn[0]
 
     def e2e_time(hl, hln, hn, steps):
@@ -429,7 +455,7 @@ def run_b200(args):
         cfg_sampler.start()
     try:
         configs["config5_mixed_merkle_2^22"] = config5(torch, dist, cp, N, BI, CudaMixedBackend, sharded_merkle_build, gold, world, rank,
-                                                       local_rank, flush, barrier, all_true)
+                                                       local_rank, flush, barrier, all_true, ex if use_fused else None)
     except Exception as e:                              # an extra, never a reason to lose the contract line
         configs["config5_mixed_merkle_2^22"] = {"error": repr(e)}
     if world == 1:
@@ -445,19 +471,24 @@ def run_b200(args):
     cfg_clocks = cfg_sampler.stop() if rank == 0 else None
 
     if rank == 0:
-        launches_per_step = merkle_launches(n_local) + ((world.bit_length() - 1) if world > 1 else 0)
+        launches_per_step = merkle_launches(ctx, n_local) + (0 if (world == 1 or use_fused) else 1)
         line = {"metric": "poseidon_perms_per_sec", "value": value, "unit": "perms/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "merkle_build_s": ms_per_step * 1e-3, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (256-bit Montgomery integer)", "data": "synthetic",
                 "config": {"workload": args.workload, "description": desc, "leaves_total": n_total, "leaves_per_gpu": n_local,
-                           "parallelism": f"leaf-sharded x{world}, one all-gather of subtree roots", "l2": "flushed (256 MB write) between timed steps",
+                           "parallelism": (f"leaf-sharded x{world}; subtree roots exchanged " +
+                                           ("inside each rank's last kernel over NVLink peer memory (CUDA IPC), top levels fused in" if use_fused
+                                            else "by one NCCL all-gather (torch.distributed)")) if world > 1 else "one GPU",
+                           "other_exchange_ms_per_step": other_ms, "other_exchange": None if world == 1 else ("nccl all-gather" if use_fused else "fused peer-memory kernel"),
+                           "l2": "flushed (256 MB write) between timed steps",
                            "perms_per_step": perms_total, "inputs": "SplitMix64 stream over the global leaf index (bench_inputs.py): identical tree at every N"},
                 "root": root_u, "root_matches_oracle": root_ok, "slices_match_single_gpu_build": slices_ok,
                 "oracle_root_source": "tests/golden/bench_goldens.json (oracle/cref via tests/golden/make_bench_goldens.py)",
                 "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
                 "e2e": {"value": e2e_value, "unit": "perms/s", "h2d_bytes_per_step": n_local * leaf_len * 32 * world,
                         "d2h_bytes_per_step": (2 * n_local - 1) * 32 * world, "steps": e2e_steps, "root_matches_oracle": e2e_root_ok,
-                        "api": "cpb_merkle_poseidon_build (host pointers, pinned)", "pageable": e2e_pageable},
+                        "api": "cpb_merkle_poseidon_build (host pointers, pinned)" if world == 1 else "cpb_merkle_poseidon_build_sharded (host pointers, pinned; root exchange inside)",
+                        "pageable": e2e_pageable},
                 "roofline": roofline, "integer_pipe": integer, "configs": configs, "configs_clocks": cfg_clocks}
         if world == 1:
             arm = CpuArm(args.workload)
@@ -574,7 +605,7 @@ def config3(torch, cp, N, BI, gold, dev_index, flush, time_kernel, integer_pipe,
                                  "(profiles/r1_ncu_pedersen_gather.txt), trading HBM bandwidth (12 % used) for half the point additions; bound by the integer multiply pipe"}}
 
 
-def config5(torch, dist, cp, N, BI, CudaMixedBackend, sharded_merkle_build, gold, world, rank, dev_index, flush, barrier, all_true):
+def config5(torch, dist, cp, N, BI, CudaMixedBackend, sharded_merkle_build, gold, world, rank, dev_index, flush, barrier, all_true, ex=None):
     """BASELINE configs[4]: Pedersen leaf CRH (x-coordinate) + Poseidon two-to-one over BLS12-381 Fr, 2^22 x 128-byte leaves,
     leaf-sharded over the ranks of this run (BASELINE names 4 GPUs); root against the committed oracle root."""
     dev = torch.device("cuda", dev_index)
@@ -585,14 +616,14 @@ def config5(torch, dist, cp, N, BI, CudaMixedBackend, sharded_merkle_build, gold
     be = CudaMixedBackend(prm, node, dev_index)
     leaves = BI.bytes_torch(torch, BI.SEED_CONFIG5, 128 * rank * n_local, 128 * n_local, dev).view(n_local, 128)
     for _ in range(2):
-        tree = sharded_merkle_build(be, leaves, gather="roots")
+        tree = sharded_merkle_build(be, leaves, gather="roots", exchange=ex)
     ts = []
     for _ in range(3):
         flush.zero_()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        tree = sharded_merkle_build(be, leaves, gather="roots")
+        tree = sharded_merkle_build(be, leaves, gather="roots", exchange=ex)
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))

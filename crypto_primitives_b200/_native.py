@@ -14,7 +14,7 @@ u64p = C.POINTER(C.c_uint64)
 u8p = C.POINTER(C.c_uint8)
 vp = C.c_void_p
 
-CPB_OK, CPB_BAD_LENGTH, CPB_BAD_PARAMS, CPB_NOT_POW2, CPB_CUDA_ERROR, CPB_NO_DEVICE, CPB_UNSUPPORTED, CPB_NULL_POINTER, CPB_INTERNAL_ERROR = range(9)
+CPB_OK, CPB_BAD_LENGTH, CPB_BAD_PARAMS, CPB_NOT_POW2, CPB_CUDA_ERROR, CPB_NO_DEVICE, CPB_UNSUPPORTED, CPB_NULL_POINTER, CPB_INTERNAL_ERROR, CPB_NCCL_ERROR = range(10)
 
 # name -> (restype, argtypes); mirrors include/cpb200.h one to one (tests/test_abi.py checks it).
 SIGNATURES = {
@@ -24,7 +24,7 @@ SIGNATURES = {
     "cpb_device_count": (C.c_int, []),
     "cpb_host_register": (C.c_int, [vp, C.c_size_t]),
     "cpb_host_unregister": (C.c_int, [vp]),
-    "cpb_merkle_poseidon_launch_count": (C.c_size_t, [C.c_size_t]),
+    "cpb_merkle_poseidon_launch_count": (C.c_size_t, [vp, C.c_size_t]),
     "cpb_field_modulus": (C.c_int, [C.c_int, u64p]),
     "cpb_field_to_montgomery": (C.c_int, [C.c_int, C.c_int, u64p, u64p, C.c_size_t]),
     "cpb_field_from_montgomery": (C.c_int, [C.c_int, C.c_int, u64p, u64p, C.c_size_t]),
@@ -73,6 +73,21 @@ SIGNATURES = {
     "cpb_merkle_pedersen_build_dev": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, vp, vp]),
     "cpb_merkle_mixed_build": (C.c_int, [vp, vp, u8p, C.c_size_t, C.c_size_t, u64p, u64p]),
     "cpb_merkle_mixed_build_dev": (C.c_int, [vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, vp]),
+    "cpb_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "cpb_exchange_destroy": (None, [vp]),
+    "cpb_exchange_world": (C.c_int, [vp]),
+    "cpb_exchange_rank": (C.c_int, [vp]),
+    "cpb_exchange_ipc_handle": (C.c_int, [vp, u8p]),
+    "cpb_exchange_connect_ipc": (C.c_int, [vp, u8p]),
+    "cpb_exchange_connect_local": (C.c_int, [C.POINTER(vp), C.c_int]),
+    "cpb_merkle_poseidon_build_sharded_dev": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, vp, vp, vp, vp]),
+    "cpb_merkle_poseidon_build_sharded": (C.c_int, [vp, vp, vp, u64p, C.c_size_t, C.c_size_t, u64p, u64p, u64p]),
+    "cpb_merkle_poseidon_from_digests_sharded_dev": (C.c_int, [vp, vp, vp, C.c_size_t, vp, vp, vp]),
+    "cpb_merkle_mixed_build_sharded_dev": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, vp, vp]),
+    "cpb_multi_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]),
+    "cpb_multi_destroy": (None, [vp]),
+    "cpb_multi_uses_nccl": (C.c_int, [vp]),
+    "cpb_merkle_poseidon_build_multi": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), u64p, C.c_size_t, C.c_size_t, u64p, u64p]),
 }
 
 

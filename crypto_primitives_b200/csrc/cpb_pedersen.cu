@@ -779,6 +779,26 @@ cpb_status cpb_merkle_mixed_build_dev(cpb_pedersen_ctx* leaf, cpb_poseidon_ctx* 
     });
 }
 
+// Sharded form of the mixed build (include/cpb200.h, "Merkle tree across several GPUs"): this rank's leaves, then the
+// Poseidon levels with the fused root exchange.
+cpb_status cpb_merkle_mixed_build_sharded_dev(cpb_pedersen_ctx* leaf, cpb_poseidon_ctx* node, cpb_exchange* ex, const uint8_t* leaves,
+                                              size_t leaf_len, size_t leaf_stride, size_t n_local, uint64_t* leaf_nodes,
+                                              uint64_t* non_leaf_nodes, uint64_t* top_nodes, void* stream) {
+    return cpb::guarded([&]() -> cpb_status {
+    CPB_TRY(ped_check(leaf));
+    if (!node) return fail(CPB_NULL_POINTER, "null context");
+    if (cpb_poseidon_ctx_field(node) != leaf->field_id || cpb_poseidon_ctx_device(node) != leaf->device)
+        return fail(CPB_BAD_PARAMS, "the Poseidon field must be the curve's base field, on the same device");
+    if (!pow2_gt1(n_local)) return fail(CPB_NOT_POW2, "the local leaf count should be a power of two greater than one (got %zu)", n_local);
+    CPB_TRY(check_len(leaf, leaf_len, false));
+    {
+        DeviceGuard g(leaf->device);
+        CPB_TRY(launch_hash(leaf, leaves, leaf_len, leaf_stride, nullptr, (u32*)leaf_nodes, n_local, 1, (cudaStream_t)stream));
+    }
+    return cpb_merkle_poseidon_from_digests_sharded_dev(node, ex, leaf_nodes, n_local, non_leaf_nodes, top_nodes, stream);
+    });
+}
+
 // ---- host-pointer entry points
 static cpb_status ped_host_hash(cpb_pedersen_ctx* c, const uint8_t* in, size_t len, size_t stride, const uint8_t* rnd,
                                 uint64_t* out, size_t n, int mode, bool commit) {

@@ -117,30 +117,47 @@ PoseidonDev to_dev(const host::PoseidonSchedule& S) {
         case CPB_BLS12_377_FR: CPB_FOR_T(Bls12_377_Fr, M, __VA_ARGS__)               \
     }
 
-// Largest batch of two-to-one hashes sent to the three-warp team kernel: beyond ~6000 hashes the GPU's 592 warp
-// schedulers are all busy with one hash per thread anyway.  CPB_TEAM_MAX overrides (0 disables).
+// Largest level (in hashes) handled by the four-warp tree-top kernel: beyond ~6000 hashes the GPU's 592 warp
+// schedulers are all busy with one hash per thread anyway, and the kernel's grid is capped at 128 CTAs of 32 hashes.
+// CPB_TEAM_MAX overrides (0 disables; values above 4096 are clamped).
 size_t team_max() {
     static long v = -1;
     if (v < 0) {
         const char* e = getenv("CPB_TEAM_MAX");
         v = e ? atol(e) : 4096;
+        if (v > 4096) v = 4096;
+        if (v < 0) v = 0;
     }
     return (size_t)v;
 }
+bool team_capable(const cpb_poseidon_ctx* c) { return c->dev.t == 3 && c->dev.cap == 1 && c->dev.alpha >= 2; }
 
-cpb_status launch_crh(cpb_poseidon_ctx* c, const u32* in, size_t len, u32* out, size_t n, cudaStream_t st, size_t n_out = 1) {
+cpb_status launch_tree_top(cpb_poseidon_ctx* c, const TopJob& J, cudaStream_t st) {
+    switch (c->field_id) {
+        case CPB_BLS12_381_FR: return launch_tree_top_f<Bls12_381_Fr>(c, J, st);
+        case CPB_BN254_FR: return launch_tree_top_f<Bn254_Fr>(c, J, st);
+        case CPB_JUBJUB_FR: return launch_tree_top_f<Jubjub_Fr>(c, J, st);
+        case CPB_BLS12_377_FR: return launch_tree_top_f<Bls12_377_Fr>(c, J, st);
+    }
+    return fail(CPB_BAD_PARAMS, "unknown field id %d", c->field_id);
+}
+
+}  // namespace
+
+namespace cpb {
+cpb_status launch_crh(cpb_poseidon_ctx* c, const u32* in, size_t len, u32* out, size_t n, cudaStream_t st, size_t n_out) {
     if (n == 0 || n_out == 0) return CPB_OK;
-    if (c->dev.t == 3 && c->dev.cap == 1 && len == 2 && n_out == 1 && n <= team_max()) {
-        switch (c->field_id) {
-            case CPB_BLS12_381_FR: return launch_team_f<Bls12_381_Fr>(c, in, out, n, st);
-            case CPB_BN254_FR: return launch_team_f<Bn254_Fr>(c, in, out, n, st);
-            case CPB_JUBJUB_FR: return launch_team_f<Jubjub_Fr>(c, in, out, n, st);
-            case CPB_BLS12_377_FR: return launch_team_f<Bls12_377_Fr>(c, in, out, n, st);
-        }
+    if (team_capable(c) && len == 2 && n_out == 1 && n <= team_max()) {
+        TopJob J;
+        J.flat_in = in; J.flat_out = out; J.n_flat = (long)n;
+        return launch_tree_top(c, J, st);
     }
     CPB_FOR_FIELD(launch_crh_ft, c, in, len, out, n_out, n, st)
     return fail(CPB_UNSUPPORTED, "state width t=%d is not built (this library: t = 2..9)", c->dev.t);
 }
+}  // namespace cpb
+
+namespace {
 cpb_status launch_verify(cpb_poseidon_ctx* c, cpb_poseidon_ctx* node, const u32* root, const u32* leaves, size_t leaf_len,
                          const u32* siblings, const u32* paths, int plen, const unsigned long long* indexes, unsigned char* ok,
                          size_t n, cudaStream_t st) {
@@ -154,37 +171,48 @@ cpb_status launch_permute(cpb_poseidon_ctx* c, const u32* in, u32* out, size_t n
     return fail(CPB_UNSUPPORTED, "state width t=%d is not built (this library: t = 2..9)", c->dev.t);
 }
 
+}  // namespace
+
+namespace cpb {
+
 cpb_status check_ctx(const cpb_poseidon_ctx* c) {
     if (!c) return fail(CPB_NULL_POINTER, "null context");
     return CPB_OK;
 }
 
-// Optional host mirrors (host-pointer entry points): when given, each subtree's stream also copies its slice of the
-// leaves in before hashing and its slices of leaf_nodes / of every level out afterwards, so PCIe transfers of one
-// subtree overlap the hashing of the others (copy engines + side streams); the top log2(S) levels follow at the end.
-struct MerkleHost {
-    const u32* leaves = nullptr;   // n * leaf_len elements
-    u32* leaf_nodes = nullptr;     // n elements
-    u32* nodes = nullptr;          // n - 1 elements
-};
-
 // Inner levels of subtree k of S (S a power of two) from the leaf digests, heap order: global level l has
 // 2^l nodes at [2^l - 1, 2^(l+1) - 1); subtree k owns the k-th 1/S of every level l >= log2 S
 // (new_with_leaf_digest, R/merkle_tree/mod.rs:424-523).  S = 1, k = 0 is the whole tree.
 cpb_status merkle_subtree_levels(cpb_poseidon_ctx* node, const u32* leaf_digests, size_t n, u32* nodes, size_t S, size_t k,
-                                 cudaStream_t st, const MerkleHost* H = nullptr) {
+                                 cudaStream_t st, const MerkleHost* H, const ExchangeDev* X) {
     int h = 0;
     while (((size_t)1 << h) < n) h++;
     int lg = 0;
     while (((size_t)1 << lg) < S) lg++;
+    const bool team = team_capable(node) && team_max() > 0;
     for (int l = h - 1; l >= lg; l--) {
         size_t cnt = ((size_t)1 << l) / S;
+        if (team && cnt <= team_max()) {
+            // every remaining level of this subtree in ONE launch (k_poseidon_tree_top), optionally with the multi-GPU
+            // root exchange and the replicated top levels fused in (X: only for the whole local tree, S == 1)
+            TopJob J;
+            J.leaf_digests = leaf_digests; J.nodes = nodes; J.h = h; J.lgS = lg; J.k = (long)k; J.l_start = l; J.l_end = lg;
+            if (X && S == 1) J.x = *X;
+            CPB_TRY(launch_tree_top(node, J, st));
+            if (H)
+                for (int q = l; q >= lg; q--) {
+                    size_t c2 = ((size_t)1 << q) / S, off = (((size_t)1 << q) - 1) + k * c2;
+                    CPB_CUDA(cudaMemcpyAsync(H->node_ptr(q, k * c2), nodes + 8 * off, c2 * 32, cudaMemcpyDeviceToHost, st));
+                }
+            return CPB_OK;
+        }
         const u32* in = (l == h - 1) ? leaf_digests + 8 * (2 * k * cnt) : nodes + 8 * ((((size_t)1 << (l + 1)) - 1) + 2 * k * cnt);
         u32* out = nodes + 8 * ((((size_t)1 << l) - 1) + k * cnt);
         CPB_TRY(launch_crh(node, in, 2, out, cnt, st));
         // copy the level out right behind its kernel: the transfer overlaps the next levels and the other subtrees
-        if (H) CPB_CUDA(cudaMemcpyAsync(H->nodes + (out - nodes), out, cnt * 32, cudaMemcpyDeviceToHost, st));
+        if (H) CPB_CUDA(cudaMemcpyAsync(H->node_ptr(l, k * cnt), out, cnt * 32, cudaMemcpyDeviceToHost, st));
     }
+    if (X && S == 1) return fail(CPB_UNSUPPORTED, "the fused root exchange needs a rate-2, capacity-1 Poseidon two-to-one hash with alpha >= 2");
     return CPB_OK;
 }
 cpb_status merkle_levels(cpb_poseidon_ctx* node, const u32* leaf_digests, size_t n, u32* nodes, cudaStream_t st) {
@@ -215,17 +243,16 @@ cpb_status ensure_side_streams(cpb_poseidon_ctx* c, size_t S) {
 }
 
 // leaf hashing (when leaves != nullptr) + all inner levels, S subtrees on S side streams joined on `st`
+// X (optional): multi-GPU build -- after the local root, exchange the roots with the peers and compute the replicated top
+// levels inside the last tree-top launch (ExchangeDev, poseidon_kernels.cuh).
 cpb_status merkle_build_streams(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, const u32* leaves, size_t leaf_len, size_t n,
-                                u32* leaf_nodes, u32* nodes, cudaStream_t st, const MerkleHost* H = nullptr) {
+                                u32* leaf_nodes, u32* nodes, cudaStream_t st, const MerkleHost* H, const ExchangeDev* X) {
     size_t S = merkle_streams(n);
     if (S <= 1) {
         if (H && H->leaves && n * leaf_len) CPB_CUDA(cudaMemcpyAsync((void*)leaves, H->leaves, n * leaf_len * 32, cudaMemcpyHostToDevice, st));
         if (leaves) CPB_TRY(launch_crh(leaf, leaves, leaf_len, leaf_nodes, n, st));
-        CPB_TRY(merkle_levels(node, leaf_nodes, n, nodes, st));
-        if (H) {
-            CPB_CUDA(cudaMemcpyAsync(H->leaf_nodes, leaf_nodes, n * 32, cudaMemcpyDeviceToHost, st));
-            CPB_CUDA(cudaMemcpyAsync(H->nodes, nodes, (n - 1) * 32, cudaMemcpyDeviceToHost, st));
-        }
+        CPB_TRY(merkle_subtree_levels(node, leaf_nodes, n, nodes, 1, 0, st, H, X));
+        if (H) CPB_CUDA(cudaMemcpyAsync(H->leaf_nodes, leaf_nodes, n * 32, cudaMemcpyDeviceToHost, st));
         return CPB_OK;
     }
     CPB_TRY(ensure_side_streams(node, S));
@@ -257,20 +284,49 @@ cpb_status merkle_build_streams(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, 
         if (done[k]) cudaEventDestroy(done[k]);
     if (rc != CPB_OK) return rc;
     if (e != cudaSuccess) return fail(CPB_CUDA_ERROR, "merkle stream fork/join failed: %s", cudaGetErrorString(e));
-    // top log2(S) levels on the caller's stream
+    // top log2(S) levels on the caller's stream: one tree-top launch (with the fused exchange when X is given)
+    int lg = 0, h = 0;
+    while (((size_t)1 << lg) < S) lg++;
+    while (((size_t)1 << h) < n) h++;
+    if (team_capable(node) && team_max() > 0) {
+        TopJob J;
+        J.leaf_digests = leaf_nodes; J.nodes = nodes; J.h = h; J.lgS = 0; J.k = 0; J.l_start = lg - 1; J.l_end = 0;
+        if (X) J.x = *X;
+        CPB_TRY(launch_tree_top(node, J, st));
+    } else {
+        if (X) return fail(CPB_UNSUPPORTED, "the fused root exchange needs a rate-2, capacity-1 Poseidon two-to-one hash with alpha >= 2");
+        for (int l = lg - 1; l >= 0; l--) {
+            size_t cnt = (size_t)1 << l;
+            CPB_TRY(launch_crh(node, nodes + 8 * ((((size_t)1 << (l + 1)) - 1)), 2, nodes + 8 * (cnt - 1), cnt, st));
+        }
+    }
+    if (H)
+        for (int l = lg - 1; l >= 0; l--)
+            CPB_CUDA(cudaMemcpyAsync(H->node_ptr(l, 0), nodes + 8 * (((size_t)1 << l) - 1), ((size_t)1 << l) * 32, cudaMemcpyDeviceToHost, st));
+    return CPB_OK;
+}
+
+// Kernel launches of merkle_build_streams(leaf != nullptr) for n leaves with this two-to-one context.
+size_t count_launches(const cpb_poseidon_ctx* node, size_t n) {
+    int h = 0;
+    while (((size_t)1 << h) < n) h++;
+    const size_t S = merkle_streams(n);
     int lg = 0;
     while (((size_t)1 << lg) < S) lg++;
-    for (int l = lg - 1; l >= 0; l--) {
-        size_t cnt = (size_t)1 << l;
-        CPB_TRY(launch_crh(node, nodes + 8 * ((((size_t)1 << (l + 1)) - 1)), 2, nodes + 8 * (cnt - 1), cnt, st));
+    const bool team = team_capable(node) && team_max() > 0;
+    size_t per_subtree = 1;                                   // the leaf hash
+    for (int l = h - 1; l >= lg; l--) {
+        size_t cnt = ((size_t)1 << l) / S;
+        if (team && cnt <= team_max()) { per_subtree += 1; break; }
+        per_subtree += 1;
     }
-    if (H && S > 1) CPB_CUDA(cudaMemcpyAsync(H->nodes, nodes, (S - 1) * 32, cudaMemcpyDeviceToHost, st));
-    return CPB_OK;
+    size_t top = S > 1 ? (team ? 1 : (size_t)lg) : 0;
+    return S * per_subtree + top;
 }
 
 bool pow2_gt1(size_t n) { return n > 1 && (n & (n - 1)) == 0; }
 
-}  // namespace
+}  // namespace cpb
 
 // ------------------------------------------------------------------------------ C ABI
 extern "C" {
@@ -291,15 +347,10 @@ int cpb_device_count(void) {
 }
 
 // Kernel launches one cpb_merkle_poseidon_build_dev over n leaves issues (leaf hash included): what bench.py reports as
-// gpu_launches.  Mirrors merkle_build_streams below.
-size_t cpb_merkle_poseidon_launch_count(size_t n) {
-    if (!pow2_gt1(n)) return 0;
-    int h = 0;
-    while (((size_t)1 << h) < n) h++;
-    size_t S = merkle_streams(n);
-    int lg = 0;
-    while (((size_t)1 << lg) < S) lg++;
-    return S > 1 ? S * (size_t)(1 + (h - lg)) + (size_t)lg : (size_t)(1 + h);
+// gpu_launches.  Mirrors merkle_build_streams above.
+size_t cpb_merkle_poseidon_launch_count(const cpb_poseidon_ctx* node_ctx, size_t n) {
+    if (!node_ctx || !pow2_gt1(n)) return 0;
+    return count_launches(node_ctx, n);
 }
 
 // Page-lock a caller-owned host buffer so that the host-pointer entry points copy at full PCIe rate and overlap with

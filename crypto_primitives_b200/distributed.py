@@ -14,8 +14,15 @@ holds the reference's complete `leaf_nodes` / `non_leaf_nodes` arrays: because t
 heap-ordered by level, rank k's nodes of global level l >= g are the k-th contiguous slice of
 that level, so each level is one in-place all_gather_into_tensor -- no repacking.
 
-One process per GPU (torchrun); torch.distributed is plumbing only.  The hashing backend is
-injected so the sharding / collective logic can be exercised on CPU with gloo (tests/test_dist_cpu.py).
+Two exchanges for step 2.  `Exchange` (default on GPUs): every rank owns a small device buffer that its
+peers map through CUDA IPC; the last kernel of the local build pushes the local root into every peer's buffer
+over NVLink, waits for theirs and computes the top levels -- steps 1-3 are one chain of launches inside
+libcpb200.so, with no host round trip and no collective call (csrc/cpb_multi.cu, k_poseidon_tree_top).
+Without an Exchange the roots go through one torch.distributed all_gather (NCCL or gloo).
+
+One process per GPU (torchrun); torch.distributed is plumbing only (rendezvous, IPC-handle exchange, the
+optional level gather).  The hashing backend is injected so the sharding / collective logic can be
+exercised on CPU with gloo (tests/test_dist_cpu.py).
 """
 from __future__ import annotations
 
@@ -23,6 +30,43 @@ from dataclasses import dataclass
 
 import torch
 import torch.distributed as dist
+
+
+class Exchange:
+    """This rank's end of the fused root exchange (cpb_exchange, include/cpb200.h): created collectively by all ranks of
+    `group`; the 64-byte CUDA-IPC handles travel through one all_gather."""
+
+    def __init__(self, device_index: int, group=None):
+        import ctypes as C
+        from . import _native as N
+        self.N = N
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = device_index
+        h = N.vp()
+        N.check(N.lib.cpb_exchange_create(device_index, self.world, self.rank, C.byref(h)))
+        self.handle = h.value
+        if self.world > 1:
+            mine = (C.c_uint8 * 64)()
+            N.check(N.lib.cpb_exchange_ipc_handle(self.handle, mine))
+            dev = torch.device("cuda", device_index)
+            src = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+            allh = torch.empty(64 * self.world, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, src, group=group)
+            buf = (C.c_uint8 * (64 * self.world))(*allh.cpu().tolist())
+            N.check(N.lib.cpb_exchange_connect_ipc(self.handle, buf))
+            dist.barrier(group=group)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.N.lib.cpb_exchange_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _log2(n: int) -> int:
@@ -64,6 +108,17 @@ class CudaPoseidonBackend:
                                                               leaf_nodes.data_ptr(), nodes.data_ptr(), self._stream()))
         return leaf_nodes, nodes
 
+    def build_sharded(self, leaves: torch.Tensor, ex: "Exchange"):
+        """Local subtree + fused root exchange + replicated top in one chain of launches:
+        -> (leaf_nodes (n,4), nodes (n-1,4) local heap order, top (world-1, 4))."""
+        n, L = leaves.shape[0], leaves.shape[1]
+        leaf_nodes = self._buf("leaf", (n, 4), leaves.device)
+        nodes = self._buf("nodes", (n - 1, 4), leaves.device)
+        top = self._buf("top", (max(ex.world - 1, 1), 4), leaves.device)
+        self.N.check(self.N.lib.cpb_merkle_poseidon_build_sharded_dev(self.leaf_ctx, self.node_ctx, ex.handle, leaves.data_ptr(), L, n,
+                                                                      leaf_nodes.data_ptr(), nodes.data_ptr(), top.data_ptr(), self._stream()))
+        return leaf_nodes, nodes, top
+
     def hash_leaves(self, leaves: torch.Tensor):
         n, L = leaves.shape[0], leaves.shape[1]
         out = self._buf("leaf", (n, 4), leaves.device)
@@ -98,6 +153,15 @@ class CudaMixedBackend(CudaPoseidonBackend):
         self.N.check(self.N.lib.cpb_merkle_mixed_build_dev(self.leaf_ctx, self.node_ctx, leaves.data_ptr(), ln, leaves.stride(0), n,
                                                            leaf_nodes.data_ptr(), nodes.data_ptr(), self._stream()))
         return leaf_nodes, nodes
+
+    def build_sharded(self, leaves: torch.Tensor, ex: "Exchange"):
+        n, ln = leaves.shape
+        leaf_nodes = self._buf("leaf", (n, 4), leaves.device)
+        nodes = self._buf("nodes", (n - 1, 4), leaves.device)
+        top = self._buf("top", (max(ex.world - 1, 1), 4), leaves.device)
+        self.N.check(self.N.lib.cpb_merkle_mixed_build_sharded_dev(self.leaf_ctx, self.node_ctx, ex.handle, leaves.data_ptr(), ln, leaves.stride(0), n,
+                                                                   leaf_nodes.data_ptr(), nodes.data_ptr(), top.data_ptr(), self._stream()))
+        return leaf_nodes, nodes, top
 
     def hash_leaves(self, leaves: torch.Tensor):
         n, ln = leaves.shape
@@ -136,8 +200,10 @@ def level_slices(n_leaves: int, world: int, rank: int):
     return out
 
 
-def sharded_merkle_build(backend, local_leaves: torch.Tensor, gather: str = "roots", group=None) -> ShardedTree:
-    """Build the tree whose leaves are the concatenation over ranks of `local_leaves` (rank order)."""
+def sharded_merkle_build(backend, local_leaves: torch.Tensor, gather: str = "roots", group=None, exchange: Exchange | None = None) -> ShardedTree:
+    """Build the tree whose leaves are the concatenation over ranks of `local_leaves` (rank order).  With `exchange` (and
+    at least two leaves per rank) the root exchange and the top levels run fused inside the library; otherwise the roots
+    go through one all_gather of torch.distributed."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     g = _log2(world)
@@ -148,6 +214,11 @@ def sharded_merkle_build(backend, local_leaves: torch.Tensor, gather: str = "roo
         raise ValueError("`leaves.len() should be power of two and greater than one")
     w = backend.digest_words
 
+    if exchange is not None and world > 1 and n_local >= 2:
+        assert exchange.world == world and exchange.rank == rank
+        leaf_nodes, nodes, top = backend.build_sharded(local_leaves, exchange)
+        tree = ShardedTree(top[0], n, world, rank, leaf_nodes, nodes, top)
+        return _gather_levels(tree, gather, group, w)
     if n_local >= 2:
         leaf_nodes, nodes = backend.build_local(local_leaves)
         local_root = nodes[0]
@@ -165,6 +236,12 @@ def sharded_merkle_build(backend, local_leaves: torch.Tensor, gather: str = "roo
         root = local_root
 
     tree = ShardedTree(root, n, world, rank, leaf_nodes, nodes, top)
+    return _gather_levels(tree, gather, group, w)
+
+
+def _gather_levels(tree: ShardedTree, gather: str, group, w: int) -> ShardedTree:
+    n, world, rank = tree.n_leaves, tree.world, tree.rank
+    leaf_nodes, nodes, top = tree.local_leaf_nodes, tree.local_nodes, tree.top_nodes
     if gather == "levels":
         full_leaf = torch.empty((n, w), dtype=leaf_nodes.dtype, device=leaf_nodes.device)
         full_nodes = torch.empty((n - 1, w), dtype=leaf_nodes.dtype, device=leaf_nodes.device)

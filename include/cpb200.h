@@ -51,7 +51,8 @@ typedef enum cpb_status {
     CPB_NO_DEVICE = 5,
     CPB_UNSUPPORTED = 6,
     CPB_NULL_POINTER = 7,
-    CPB_INTERNAL_ERROR = 8   /* host allocation failure or any C++ exception caught at the boundary */
+    CPB_INTERNAL_ERROR = 8,  /* host allocation failure or any C++ exception caught at the boundary */
+    CPB_NCCL_ERROR = 9       /* libnccl could not be loaded, or an NCCL call of the multi-GPU build failed */
 } cpb_status;
 
 typedef enum cpb_field {
@@ -70,6 +71,8 @@ typedef enum cpb_curve {
 typedef struct cpb_poseidon_ctx cpb_poseidon_ctx;
 typedef struct cpb_pedersen_ctx cpb_pedersen_ctx;
 typedef struct cpb_bowe_hopwood_ctx cpb_bowe_hopwood_ctx;
+typedef struct cpb_exchange cpb_exchange;   /* one rank's end of the multi-GPU root exchange (one process per GPU) */
+typedef struct cpb_multi cpb_multi;         /* a group of GPUs driven by one process */
 
 const char* cpb_last_error(void);
 
@@ -155,8 +158,9 @@ cpb_status cpb_merkle_poseidon_build(cpb_poseidon_ctx* leaf_ctx, cpb_poseidon_ct
 cpb_status cpb_merkle_poseidon_build_dev(cpb_poseidon_ctx* leaf_ctx, cpb_poseidon_ctx* node_ctx,
                                          const uint64_t* leaves, size_t leaf_len, size_t n, uint64_t* leaf_nodes,
                                          uint64_t* non_leaf_nodes, void* stream);
-/* Number of kernel launches one cpb_merkle_poseidon_build_dev over n leaves issues (0 when n is not a power of two > 1). */
-size_t cpb_merkle_poseidon_launch_count(size_t n);
+/* Number of kernel launches one cpb_merkle_poseidon_build_dev over n leaves issues with this two-to-one context
+ * (0 when n is not a power of two > 1). */
+size_t cpb_merkle_poseidon_launch_count(const cpb_poseidon_ctx* node_ctx, size_t n);
 /* MerkleTree::new_with_leaf_digest (mod.rs:424-523): inner levels only. */
 cpb_status cpb_merkle_poseidon_from_digests(cpb_poseidon_ctx* node_ctx, const uint64_t* leaf_digests, size_t n,
                                             uint64_t* non_leaf_nodes);
@@ -262,6 +266,61 @@ cpb_status cpb_merkle_mixed_build(cpb_pedersen_ctx* leaf_ctx, cpb_poseidon_ctx* 
 cpb_status cpb_merkle_mixed_build_dev(cpb_pedersen_ctx* leaf_ctx, cpb_poseidon_ctx* node_ctx, const uint8_t* leaves,
                                       size_t leaf_len, size_t leaf_stride, size_t n, uint64_t* leaf_nodes,
                                       uint64_t* non_leaf_nodes, void* stream);
+
+/* ---- Merkle tree across several GPUs ------------------------------------------------------------ */
+/* The reference builds a tree in one process (MerkleTree::new, R/merkle_tree/mod.rs:411-523).  On G = 2^g GPUs the leaves
+ * are sharded contiguously: rank k owns leaves [k*n/G, (k+1)*n/G), builds that subtree (its nodes in LOCAL heap order, as
+ * if it were a tree of its own), the G subtree roots are exchanged once and every rank computes the g top levels
+ * (`top_nodes`: G-1 digests in heap order, root first).  Because the reference's node array is heap-ordered by level,
+ * local level l of rank k is the k-th contiguous slice of global level l+g.  Two-to-one hash: poseidon::TwoToOneCRH
+ * (rate 2, capacity 1, alpha >= 2).
+ *
+ * (a) One process per GPU.  Each rank creates a cpb_exchange on its device, publishes its 64-byte CUDA-IPC handle to the
+ * others by any means (torch.distributed, MPI, a file), and connects.  The *_sharded calls are collective: every rank
+ * issues them in the same order.  The last kernel of the local build pushes the rank's root into every peer's exchange
+ * buffer over NVLink (peer stores), waits for theirs and computes the top levels -- no host round trip, no second launch.
+ * (b) One process, several GPUs: the cpb_multi group further down. */
+cpb_status cpb_exchange_create(int device, int world, int rank, cpb_exchange** out);
+void cpb_exchange_destroy(cpb_exchange* ex);
+int cpb_exchange_world(const cpb_exchange* ex);
+int cpb_exchange_rank(const cpb_exchange* ex);
+cpb_status cpb_exchange_ipc_handle(cpb_exchange* ex, uint8_t handle_out[64]);
+/* handles: world x 64 bytes, entry r = rank r's handle (the own entry is ignored). */
+cpb_status cpb_exchange_connect_ipc(cpb_exchange* ex, const uint8_t* handles);
+/* All `world` exchanges live in THIS process (all[r] has rank r): enables peer access and wires them directly. */
+cpb_status cpb_exchange_connect_local(cpb_exchange** all, int world);
+
+/* This rank's part of MerkleTree::new: leaves (n_local x leaf_len elements, n_local a power of two > 1) -> leaf_nodes
+ * [n_local], non_leaf_nodes [n_local - 1] (local heap order), top_nodes [world - 1] (identical on every rank; unused
+ * when world == 1).  _dev: device pointers on the exchange's device, asynchronous on `stream`. */
+cpb_status cpb_merkle_poseidon_build_sharded_dev(cpb_poseidon_ctx* leaf_ctx, cpb_poseidon_ctx* node_ctx, cpb_exchange* ex,
+                                                 const uint64_t* leaves, size_t leaf_len, size_t n_local, uint64_t* leaf_nodes,
+                                                 uint64_t* non_leaf_nodes, uint64_t* top_nodes, void* stream);
+cpb_status cpb_merkle_poseidon_build_sharded(cpb_poseidon_ctx* leaf_ctx, cpb_poseidon_ctx* node_ctx, cpb_exchange* ex,
+                                             const uint64_t* leaves, size_t leaf_len, size_t n_local, uint64_t* leaf_nodes,
+                                             uint64_t* non_leaf_nodes, uint64_t* top_nodes);
+/* new_with_leaf_digest, sharded: this rank's leaf digests -> its inner nodes + the replicated top (used by the mixed tree). */
+cpb_status cpb_merkle_poseidon_from_digests_sharded_dev(cpb_poseidon_ctx* node_ctx, cpb_exchange* ex, const uint64_t* leaf_digests,
+                                                        size_t n_local, uint64_t* non_leaf_nodes, uint64_t* top_nodes, void* stream);
+/* BASELINE config 5, sharded: Pedersen leaf hash (x-coordinate) + Poseidon levels; see cpb_merkle_mixed_build_dev. */
+cpb_status cpb_merkle_mixed_build_sharded_dev(cpb_pedersen_ctx* leaf_ctx, cpb_poseidon_ctx* node_ctx, cpb_exchange* ex,
+                                              const uint8_t* leaves, size_t leaf_len, size_t leaf_stride, size_t n_local,
+                                              uint64_t* leaf_nodes, uint64_t* non_leaf_nodes, uint64_t* top_nodes, void* stream);
+
+/* (b) One process, several GPUs.  `devices`: ndev distinct device ids, ndev a power of two.  The root exchange is the fused
+ * peer-memory kernel when every pair of devices has peer access, otherwise (or with CPB_MULTI_EXCHANGE=nccl in the
+ * environment) one ncclAllGather of the subtree roots over communicators from ncclCommInitAll; libnccl.so.2 is loaded on
+ * first use (CPB_NCCL_ERROR when it is missing or a call fails). */
+cpb_status cpb_multi_create(int ndev, const int* devices, cpb_multi** out);
+void cpb_multi_destroy(cpb_multi* m);
+int cpb_multi_uses_nccl(const cpb_multi* m);
+/* MerkleTree::new (R/merkle_tree/mod.rs:411-422) over HOST arrays in the reference's layout -- leaves: n x leaf_len
+ * elements; leaf_nodes[n]; non_leaf_nodes[n-1] in GLOBAL heap order -- computed on the ndev devices of `m`:
+ * leaf_ctxs[d] / node_ctxs[d] are contexts of the same parameters created on devices[d].  Copies are pipelined with the
+ * hashing per device; one host thread per device.  n / ndev must be >= 2. */
+cpb_status cpb_merkle_poseidon_build_multi(cpb_multi* m, cpb_poseidon_ctx* const* leaf_ctxs, cpb_poseidon_ctx* const* node_ctxs,
+                                           const uint64_t* leaves, size_t leaf_len, size_t n, uint64_t* leaf_nodes,
+                                           uint64_t* non_leaf_nodes);
 
 #ifdef __cplusplus
 }

@@ -134,21 +134,24 @@ extern "C" int host_poseidon_verify(int field, int rate, int cap, int rf, int rp
     return 0;
 }
 
-// CPU model of the three-warp team kernel (poseidon_team.cuh): phases run for w = 0, 1, 2 in sequence per round.
+// CPU model of the four-warp team kernel (poseidon_team.cuh): each phase runs for w = 0..3 in sequence, i.e. the barrier
+// after every phase is modelled exactly; slots start poisoned so that a read of a never-written slot shows.
 template <class F> static void run_team(const PoseidonDev& D, const u32* cs, const u32* pairs, long n, u32* out) {
     u32 pm[8];
     ld_elem(pm, cs + 8 * D.off_mod);
-    int top_bit = 0;
-    for (int i = 63; i > 0; i--) if ((D.alpha >> i) & 1) { top_bit = i; break; }
+    int tb_alpha = 0, tb_e = 0;
+    for (int i = 63; i > 0; i--) if ((D.alpha >> i) & 1) { tb_alpha = i; break; }
+    for (int i = 63; i > 0; i--) if (((D.alpha - 1) >> i) & 1) { tb_e = i; break; }
     std::vector<u32> xb(kTeamXbWords, 0xdeadbeefu);
     for (long i = 0; i < n; i++) {
-        u32 s[3][8];
-        fp_zero(s[0]);
+        u32 s[4][8], t[4][8];
+        for (int w = 0; w < 4; w++) { fp_zero(s[w]); fp_zero(t[w]); }
         for (int j = 0; j < 8; j++) { s[1][j] = pairs[16 * i + j]; s[2][j] = pairs[16 * i + 8 + j]; }
         const int lane = (int)(i & 31);
         for (int r = 0; r < D.rf + D.rp; r++) {
-            for (int w = 0; w < 3; w++) team_phase_a<F>(s[w], w, lane, r, D, cs, pm, xb.data(), top_bit);
-            for (int w = 0; w < 3; w++) team_phase_b<F>(s[w], w, lane, r, D, cs, pm, xb.data());
+            for (int w = 0; w < 4; w++) team_phase1<F>(s[w], t[w], w, lane, r, D, cs, pm, xb.data(), tb_alpha, tb_e);
+            for (int w = 0; w < 4; w++) team_phase2<F>(s[w], t[w], w, lane, r, D, cs, pm, xb.data());
+            for (int w = 0; w < 4; w++) team_publish<F>(s[w], w, lane, r, D, cs, xb.data());
         }
         for (int j = 0; j < 8; j++) out[8 * i + j] = s[1][j];
     }

@@ -25,7 +25,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     # the status codes of the header and of the ctypes binding agree
     status_enum = hdr[hdr.index("typedef enum cpb_status"):hdr.index("} cpb_status;")]
     codes = dict(re.findall(r"(CPB_[A-Z0-9_]+) = (\d+)", status_enum))
-    assert len(codes) == 9
+    assert len(codes) == 10
     for name, value in codes.items():
         assert getattr(N, name) == int(value), name
 

@@ -25,6 +25,9 @@ def test_reference_arm_prints_one_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "perms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and line["steps"] == 1 and line["warmup"] == 0
+    # the CPU arm's tree is the first 1/16 of the 2^24-leaf job: its root is node 15 of the committed oracle tree
+    assert line["cpu_baseline"]["root_matches_oracle_golden"] is True
+    assert line["cpu_baseline"]["host"]["threads"] == line["cpu_baseline"]["cores"]
 
 
 def test_reference_arm_other_ranks_stay_silent():

@@ -83,8 +83,9 @@ def test_small_mixed_tree_and_sampled_pedersen_outputs():
 
 
 def test_launch_count_and_host_pinning_helpers():
-    assert N.lib.cpb_merkle_poseidon_launch_count(3) == 0
-    assert N.lib.cpb_merkle_poseidon_launch_count(1 << 24) > 24
+    ctx = bench.poseidon_params(cp, "bn254").context(0)
+    assert N.lib.cpb_merkle_poseidon_launch_count(ctx, 3) == 0
+    assert 8 < N.lib.cpb_merkle_poseidon_launch_count(ctx, 1 << 24) < 200
     a = np.zeros(1 << 16, dtype=np.uint64)
     N.check(N.lib.cpb_host_register(a.ctypes.data, a.nbytes))
     N.check(N.lib.cpb_host_unregister(a.ctypes.data))

@@ -170,3 +170,79 @@ def test_batched_path_verification():
     assert not tree.verify_proofs_batch(proofs[:64], leaves[:64], wrong_root).any()
     # agrees with the single-path mirror of Path::verify
     assert proofs[100].verify(cfg, cfg, tree.root(), leaves[100])
+
+
+def _oracle_tree(which, n, seed):
+    _, ocfg = oracle_config(which)
+    leaves = synth_elems(seed, (n, 2), ocfg.p)
+    O = cref.Poseidon(ocfg)
+    ln, nn = cref.poseidon_merkle(O, O, leaves, threads=8)
+    return leaves, ln, nn
+
+
+@pytest.mark.parametrize("which,world,logn", [("bn254_r2", 2, 6), ("bls_default_r2", 4, 12), ("bn254_r2", 8, 16), ("jubjub_merkle_fixture", 2, 18)])
+def test_fused_root_exchange_with_all_ranks_on_one_gpu(which, world, logn):
+    """The multi-GPU build's last kernel (k_poseidon_tree_top: local top levels + push of the root into every peer's
+    exchange buffer + wait + replicated top) with all `world` ranks on THIS device, each on its own stream: the same code
+    that runs over NVLink peer memory, testable on a one-GPU box.  Every rank's arrays against the oracle."""
+    import ctypes as C
+    import torch
+    from crypto_primitives_b200 import _native as N
+    from crypto_primitives_b200.distributed import level_slices
+    cfg = product_config(which)
+    n = 1 << logn
+    per = n // world
+    leaves, exp_leaf, exp_nodes = _oracle_tree(which, n, 4242 + logn)
+    ctx = cfg.context(0)
+    exs = (N.vp * world)()
+    for r in range(world):
+        h = N.vp()
+        N.check(N.lib.cpb_exchange_create(0, world, r, C.byref(h)))
+        exs[r] = h.value
+    N.check(N.lib.cpb_exchange_connect_local(exs, world))
+    try:
+        dev = torch.device("cuda", 0)
+        d_leaves = torch.from_numpy(np.ascontiguousarray(leaves).view(np.int64)).to(dev)
+        streams = [torch.cuda.Stream(dev) for _ in range(world)]
+        outs = []
+        for rep in range(3):                                   # the epoch / parity logic: several collective calls in a row
+            outs = []
+            for r in range(world):
+                ln = torch.zeros((per, 4), dtype=torch.int64, device=dev)
+                nn = torch.zeros((per - 1, 4), dtype=torch.int64, device=dev)
+                top = torch.zeros((world - 1, 4), dtype=torch.int64, device=dev)
+                outs.append((ln, nn, top))
+            torch.cuda.synchronize()
+            for r in reversed(range(world)):                   # enqueue everything first, never wait in between
+                N.check(N.lib.cpb_merkle_poseidon_build_sharded_dev(ctx, ctx, exs[r], d_leaves[r * per:(r + 1) * per].data_ptr(), 2, per,
+                                                                    outs[r][0].data_ptr(), outs[r][1].data_ptr(), outs[r][2].data_ptr(),
+                                                                    streams[r].cuda_stream))
+            torch.cuda.synchronize()
+        for r in range(world):
+            ln, nn, top = (t.cpu().numpy().view(np.uint64) for t in outs[r])
+            assert np.array_equal(ln, exp_leaf[r * per:(r + 1) * per])
+            for gstart, cnt, lstart in level_slices(n, world, r):
+                assert np.array_equal(nn[lstart:lstart + cnt], exp_nodes[gstart:gstart + cnt]), (r, gstart)
+            assert np.array_equal(top, exp_nodes[:world - 1]), r
+    finally:
+        for r in range(world):
+            N.lib.cpb_exchange_destroy(exs[r])
+
+
+def test_tree_top_kernel_handles_every_small_shape():
+    """from_digests for every n = 2 .. 2^14 power of two: the levels at or below 4096 hashes run in ONE launch of the
+    four-warp tree-top kernel (per-CTA progress flags between levels); n > 8192 adds bulk launches above it."""
+    cfg = product_config("bls_default_r2")
+    _, ocfg = oracle_config("bls_default_r2")
+    O = cref.Poseidon(ocfg)
+    for logn in range(1, 15):
+        n = 1 << logn
+        d = synth_elems(900 + logn, (n,), ocfg.p)
+        exp = []
+        cur = d
+        while len(cur) > 1:
+            cur = O.compress_batch(cur.reshape(-1, 2, 4), threads=4)
+            exp.insert(0, cur)
+        exp = np.concatenate(exp)
+        got = MerkleTree.new_with_leaf_digest(cfg, cfg, d).non_leaf_nodes
+        assert np.array_equal(got, exp), logn
