@@ -5,7 +5,11 @@ The build (MerkleTree::new, mod.rs:411-523) runs on the GPU: one kernel hashes a
 launch per level compresses contiguous child pairs of the heap-ordered node array.  The tree object
 keeps the reference's two arrays -- leaf_nodes[n] and non_leaf_nodes[n-1] (root at 0, children of i
 at 2i+1 / 2i+2, mod.rs:383-395) -- on the host, so proofs are index arithmetic exactly as in
-mod.rs:547-623; verification and update re-hash through the same GPU entry points.
+mod.rs:547-623.  Verification and update are LEVEL-SYNCHRONOUS device batches for every Config: all paths
+(or all touched nodes) of one tree level go through ONE two-to-one batch call, so k proofs / k updated
+leaves cost height launches, not k * height (`verify_paths_batch`, `MultiPath.verify`, `update_batch`);
+the Poseidon field-leaf Config additionally has a single-launch kernel that recomputes one root per
+thread (`cpb_merkle_poseidon_verify_batch`).
 """
 from __future__ import annotations
 
@@ -58,7 +62,7 @@ class Config:
             nodes[start:upper] = self.two_to_one_batch(two_to_one_param, self._pairs(nodes[upper:2 * upper + 1]), device)
         return nodes
 
-    def default_leaf_digest(self):
+    def default_leaf_digest(self, leaf_param=None):
         return np.zeros(self.digest_words, dtype=np.uint64)
 
 
@@ -121,8 +125,12 @@ class PedersenByteConfig(Config):
     def build_from_digests(self, two_to_one_param, leaf_digests, device):
         return Config.build_from_digests(self, two_to_one_param, np.asarray(leaf_digests, dtype=np.uint64).reshape(-1, 2, 4), device)
 
-    def default_leaf_digest(self):
-        raise NotImplementedError("Affine::default() (the identity) is not representable as an input digest here")
+    def default_leaf_digest(self, leaf_param=None):
+        """C::Affine::default() -- the identity (0, 1) of the twisted-Edwards curve (ark-ec `Affine::zero()`, dep), which the
+        ByteDigestConverter serialises like any other point (mod.rs:71-78): MerkleTree::blank works for byte-digest Configs."""
+        from .curves import JUBJUB
+        curve = leaf_param.curve if leaf_param is not None else JUBJUB
+        return curve.base_field.elements([0, 1]).reshape(2, 4)
 
 
 class PedersenPoseidonConfig(Config):
@@ -202,6 +210,36 @@ def convert_index_to_last_level(index, height):
     return index + (1 << (height - 1)) - 1
 
 
+def _select_and_hash(cfg: Config, two_to_one_params, cur, sib, on_right, device):
+    """select_left_right_child (mod.rs:214-228) for a whole batch, then ONE two-to-one call: row i hashes (cur_i, sib_i),
+    swapped where on_right[i] (the computed node is the right child)."""
+    cur = np.asarray(cur, dtype=np.uint64)
+    sib = np.asarray(sib, dtype=np.uint64)
+    flag = np.asarray(on_right, dtype=bool).reshape((-1,) + (1,) * (cur.ndim - 1))
+    pairs = np.stack([np.where(flag, sib, cur), np.where(flag, cur, sib)], axis=1)
+    return cfg.two_to_one_batch(two_to_one_params, np.ascontiguousarray(pairs), device)
+
+
+def verify_paths_batch(leaf_hash_params, two_to_one_params, root_hash, leaves, proofs, config: Config = None, device: int = 0) -> np.ndarray:
+    """n x Path::verify (mod.rs:172-212) for any Config as device batches: one leaf-hash batch, then one two-to-one batch
+    per tree level for ALL n paths (height launches in total).  `proofs`: Paths of one tree; returns a bool array."""
+    cfg = config or PoseidonFieldConfig()
+    n = len(proofs)
+    if n == 0:
+        return np.zeros(0, dtype=bool)
+    plen = len(proofs[0].auth_path)
+    assert all(len(p.auth_path) == plen for p in proofs), "paths of different heights"
+    claimed = cfg.leaf_hash_batch(leaf_hash_params, np.asarray(leaves), device)
+    idx = np.array([p.leaf_index for p in proofs], dtype=np.int64)
+    cur = _select_and_hash(cfg, two_to_one_params, claimed, np.stack([p.leaf_sibling_hash for p in proofs]), idx & 1, device)
+    idx >>= 1
+    for level in range(plen - 1, -1, -1):
+        cur = _select_and_hash(cfg, two_to_one_params, cur, np.stack([p.auth_path[level] for p in proofs]), idx & 1, device)
+        idx >>= 1
+    root = np.asarray(root_hash, dtype=np.uint64).reshape(1, -1)
+    return np.all(np.asarray(cur).reshape(n, -1) == root, axis=1)
+
+
 @dataclass
 class Path:
     """mod.rs:139-152."""
@@ -210,18 +248,21 @@ class Path:
     leaf_index: int
 
     def verify(self, leaf_hash_params, two_to_one_params, root_hash, leaf, config: Config = None, device: int = 0) -> bool:
-        """Path::verify, mod.rs:172-212."""
+        """Path::verify, mod.rs:172-212.  Field-leaf Poseidon Config: ONE kernel launch recomputes the root
+        (cpb_merkle_poseidon_verify_batch with n = 1); other Configs: the level-synchronous batch with n = 1."""
         cfg = config or PoseidonFieldConfig()
-        claimed = cfg.leaf_hash_batch(leaf_hash_params, np.asarray(leaf)[None], device)[0]
-        l, r = (claimed, self.leaf_sibling_hash) if self.leaf_index & 1 == 0 else (self.leaf_sibling_hash, claimed)
-        cur = cfg.two_to_one_batch(two_to_one_params, np.stack([l, r])[None], device)[0]
-        index = self.leaf_index >> 1
-        for level in range(len(self.auth_path) - 1, -1, -1):
-            sib = self.auth_path[level]
-            l, r = (cur, sib) if index & 1 == 0 else (sib, cur)
-            cur = cfg.two_to_one_batch(two_to_one_params, np.stack([l, r])[None], device)[0]
-            index >>= 1
-        return bool(np.array_equal(cur, np.asarray(root_hash, dtype=np.uint64)))
+        if type(cfg) is PoseidonFieldConfig:
+            lv = np.ascontiguousarray(np.asarray(leaf, dtype=np.uint64).reshape(1, -1, 4))
+            plen = len(self.auth_path)
+            sib = np.ascontiguousarray(np.asarray(self.leaf_sibling_hash, dtype=np.uint64).reshape(1, 4))
+            paths = np.ascontiguousarray(np.stack(self.auth_path).astype(np.uint64).reshape(1, plen, 4)) if plen else np.zeros((1, 0, 4), dtype=np.uint64)
+            idx = np.array([self.leaf_index], dtype=np.uint64)
+            root = np.ascontiguousarray(root_hash, dtype=np.uint64)
+            ok = np.zeros(1, dtype=np.uint8)
+            N.check(N.lib.cpb_merkle_poseidon_verify_batch(leaf_hash_params.context(device), two_to_one_params.context(device), _p(root), _p(lv),
+                                                           lv.shape[1], _p(sib), _p(paths), plen, _p(idx), ok.ctypes.data_as(N.u8p), 1))
+            return bool(ok[0])
+        return bool(verify_paths_batch(leaf_hash_params, two_to_one_params, root_hash, np.asarray(leaf)[None], [self], cfg, device)[0])
 
 
 @dataclass
@@ -235,32 +276,36 @@ class MultiPath:
     def verify(self, leaf_hash_params, two_to_one_params, root_hash, leaves, config: Config = None, device: int = 0) -> bool:
         """MultiPath::verify, mod.rs:262-331 (with the same lookup table of already hashed nodes)."""
         cfg = config or PoseidonFieldConfig()
-        height = len(self.auth_paths_suffixes[0]) + 2
-        lut = {}
-        prev = list(self.auth_paths_suffixes[0])
-        root = np.asarray(root_hash, dtype=np.uint64)
-        claimed_all = cfg.leaf_hash_batch(leaf_hash_params, np.asarray(leaves), device)
-        for i, leaf_index in enumerate(self.leaf_indexes):
+        n = len(self.leaf_indexes)
+        if n == 0:
+            return True
+        plen = len(self.auth_paths_suffixes[0])
+        # decode the front-incremental auth paths (prefix_decode_path, mod.rs:289-297); host index work only
+        paths, prev = [], list(self.auth_paths_suffixes[0])
+        for i in range(n):
             k = self.auth_paths_prefix_lenghts[i]
             auth = list(self.auth_paths_suffixes[i]) if k == 0 else prev[:k] + list(self.auth_paths_suffixes[i])
+            assert len(auth) == plen, "auth paths of different lengths"
+            paths.append(auth)
             prev = auth
-            claimed, sib = claimed_all[i], self.leaf_siblings_hashes[i]
-            l, r = (claimed, sib) if leaf_index & 1 == 0 else (sib, claimed)
-            index = leaf_index >> 1
-            in_tree = parent(convert_index_to_last_level(leaf_index, height))
-            if in_tree not in lut:
-                lut[in_tree] = cfg.two_to_one_batch(two_to_one_params, np.stack([l, r])[None], device)[0]
-            cur = lut[in_tree]
-            for level in range(len(auth) - 1, -1, -1):
-                l, r = (cur, auth[level]) if index & 1 == 0 else (auth[level], cur)
-                index >>= 1
-                in_tree = parent(in_tree)
-                if in_tree not in lut:
-                    lut[in_tree] = cfg.two_to_one_batch(two_to_one_params, np.stack([l, r])[None], device)[0]
-                cur = lut[in_tree]
-            if not np.array_equal(cur, root):
-                return False
-        return True
+        idx = np.array(self.leaf_indexes, dtype=np.int64)
+        claimed = cfg.leaf_hash_batch(leaf_hash_params, np.asarray(leaves), device)
+        # Level-synchronous form of the reference's loop with its look-up table of already hashed nodes (mod.rs:272-322):
+        # at every level each tree node is hashed ONCE, from the first path (in order) that reaches it -- exactly the
+        # `hash_lut.entry(..).or_insert_with(..)` semantics -- and all distinct nodes of a level are one device batch.
+        node = idx >> 1                                        # position of the path's node within its level
+        uniq, first, inverse = np.unique(node, return_index=True, return_inverse=True)
+        vals = _select_and_hash(cfg, two_to_one_params, np.asarray(claimed)[first], np.stack(self.leaf_siblings_hashes)[first], idx[first] & 1, device)
+        cur = np.asarray(vals)[inverse]
+        for level in range(plen - 1, -1, -1):
+            sib = np.stack([p[level] for p in paths])
+            on_right = node & 1
+            node = node >> 1
+            uniq, first, inverse = np.unique(node, return_index=True, return_inverse=True)
+            vals = _select_and_hash(cfg, two_to_one_params, cur[first], sib[first], on_right[first], device)
+            cur = np.asarray(vals)[inverse]
+        root = np.asarray(root_hash, dtype=np.uint64).reshape(1, -1)
+        return bool(np.all(cur.reshape(n, -1) == root))
 
 
 class MerkleTree:
@@ -279,7 +324,8 @@ class MerkleTree:
     def blank(cls, leaf_hash_param, two_to_one_hash_param, height: int, config: Config = None, device: int = 0):
         """mod.rs:400-408: all leaf digests = LeafDigest::default()."""
         cfg = config or PoseidonFieldConfig()
-        d = np.tile(cfg.default_leaf_digest(), (1 << (height - 1), 1))
+        one = np.asarray(cfg.default_leaf_digest(leaf_hash_param), dtype=np.uint64)
+        d = np.ascontiguousarray(np.broadcast_to(one, (1 << (height - 1),) + one.shape))
         return cls.new_with_leaf_digest(leaf_hash_param, two_to_one_hash_param, d, cfg, device)
 
     @classmethod
@@ -344,19 +390,40 @@ class MerkleTree:
             prev = path
         return MultiPath(sibs, prefix, suffixes, idx)
 
+    def generate_proofs_batch(self, indexes):
+        """generate_proof (mod.rs:547-575) for many leaves at once as arrays: (leaf_sibling_hashes (k, ...), auth_paths
+        (k, height-2, ...) root side first, leaf_indexes (k,)).  Pure index arithmetic on the heap-ordered arrays, vectorised:
+        the sibling of the path node at depth d is node ((2^d - 1) + ((i >> (h-1-d)) ^ 1))."""
+        idx = np.asarray(indexes, dtype=np.int64).reshape(-1)
+        h1 = self._height - 1                                      # depth of the leaf level
+        sib = self.leaf_nodes[idx ^ 1]
+        cols = [self.non_leaf_nodes[((1 << d) - 1) + ((idx >> (h1 - d)) ^ 1)] for d in range(1, h1)]
+        paths = np.stack(cols, axis=1) if cols else np.zeros((idx.size, 0) + self.non_leaf_nodes.shape[1:], dtype=np.uint64)
+        return sib, paths, idx.astype(np.uint64)
+
     def verify_proofs_batch(self, proofs, leaves, root_hash=None) -> np.ndarray:
         """Many Path::verify (mod.rs:172-212) in one kernel launch (field-leaf Config): proofs = list of Path for
-        `leaves[i]`; returns a bool array.  One GPU thread recomputes one root."""
+        `leaves[i]`, or the (siblings, paths, indexes) arrays of generate_proofs_batch; returns a bool array.
+        One GPU thread recomputes one root."""
         if not isinstance(self.config, PoseidonFieldConfig):
-            raise NotImplementedError("batched verification is implemented for the Poseidon field-leaf Config")
-        n = len(proofs)
+            raise NotImplementedError("the one-launch kernel is for the Poseidon field-leaf Config; use verify_paths_batch")
         lv = np.ascontiguousarray(leaves, dtype=np.uint64)
-        assert lv.shape[0] == n and lv.ndim == 3
         plen = self._height - 2
+        if isinstance(proofs, tuple):
+            sib, paths, idx = (np.ascontiguousarray(a, dtype=np.uint64) for a in proofs)
+            n = idx.shape[0]
+            assert lv.shape[0] == n and lv.ndim == 3 and paths.shape == (n, plen, 4)
+            return self._verify_arrays(lv, sib, paths, idx, root_hash)
+        n = len(proofs)
+        assert lv.shape[0] == n and lv.ndim == 3
         sib = np.ascontiguousarray(np.stack([p.leaf_sibling_hash for p in proofs]), dtype=np.uint64)
         paths = np.ascontiguousarray(np.stack([np.stack(p.auth_path) if plen else np.zeros((0, 4), dtype=np.uint64) for p in proofs]),
                                      dtype=np.uint64).reshape(n, plen, 4)
         idx = np.array([p.leaf_index for p in proofs], dtype=np.uint64)
+        return self._verify_arrays(lv, sib, paths, idx, root_hash)
+
+    def _verify_arrays(self, lv, sib, paths, idx, root_hash):
+        n, plen = idx.shape[0], self._height - 2
         root = np.ascontiguousarray(self.root() if root_hash is None else root_hash, dtype=np.uint64)
         ok = np.zeros(n, dtype=np.uint8)
         N.check(N.lib.cpb_merkle_poseidon_verify_batch(self.leaf_hash_param.context(self.device), self.two_to_one_hash_param.context(self.device),
@@ -364,40 +431,59 @@ class MerkleTree:
                                                        ok.ctypes.data_as(N.u8p), n))
         return ok.astype(bool)
 
-    def _updated_path(self, index: int, new_leaf):
-        """mod.rs:627-677."""
+    def _updated_nodes(self, indexes, new_leaves):
+        """The nodes that change when leaves `indexes` (distinct) are replaced by `new_leaves` (mod.rs:627-677 for one leaf):
+        -> (new leaf digests, [(heap indexes, new values)] bottom level first).  Level-synchronous: the new leaves are one
+        leaf-hash batch and all touched nodes of a level one two-to-one batch -- height launches for any number of leaves."""
         cfg, dev = self.config, self.device
-        new_hash = cfg.leaf_hash_batch(self.leaf_hash_param, np.asarray(new_leaf)[None], dev)[0]
-        l, r = (new_hash, self.leaf_nodes[index + 1]) if index & 1 == 0 else (self.leaf_nodes[index - 1], new_hash)
-        path = [cfg.two_to_one_batch(self.two_to_one_hash_param, np.stack([l, r])[None], dev)[0]]
-        prev = parent(convert_index_to_last_level(index, self._height))
-        while not is_root(prev):
-            sib = self.non_leaf_nodes[sibling(prev)]
-            l, r = (path[-1], sib) if is_left_child(prev) else (sib, path[-1])
-            path.append(cfg.two_to_one_batch(self.two_to_one_hash_param, np.stack([l, r])[None], dev)[0])
-            prev = parent(prev)
-        path.reverse()
-        return new_hash, path
+        idx = np.asarray(indexes, dtype=np.int64).reshape(-1)
+        n = self.leaf_nodes.shape[0]
+        assert idx.size and idx.min() >= 0 and idx.max() < n, "index out of range"
+        assert np.unique(idx).size == idx.size, "indexes must be distinct"
+        new_hash = np.asarray(cfg.leaf_hash_batch(self.leaf_hash_param, np.asarray(new_leaves), dev))
+        par = np.unique(idx >> 1)                                  # touched leaf pairs
+        pairs = np.stack([self.leaf_nodes[2 * par], self.leaf_nodes[2 * par + 1]], axis=1)     # gathers only the touched rows
+        pairs[np.searchsorted(par, idx >> 1), idx & 1] = new_hash                              # ... with the new digests patched in
+        vals = np.asarray(cfg.two_to_one_batch(self.two_to_one_hash_param, np.ascontiguousarray(pairs), dev))
+        ids = par + (n // 2 - 1)                                   # heap indexes of the bottom inner level
+        changes = [(ids, vals)]
+        while ids[0] != 0:
+            par = np.unique((ids - 1) >> 1)
+            pairs = np.stack([self.non_leaf_nodes[2 * par + 1], self.non_leaf_nodes[2 * par + 2]], axis=1)
+            pairs[np.searchsorted(par, (ids - 1) >> 1), (ids - 1) & 1] = vals
+            vals = np.asarray(cfg.two_to_one_batch(self.two_to_one_hash_param, np.ascontiguousarray(pairs), dev))
+            ids = par
+            changes.append((ids, vals))
+        return idx, new_hash, changes
+
+    def _apply(self, idx, new_hash, changes):
+        self.leaf_nodes[idx] = new_hash
+        for ids, vals in changes:
+            self.non_leaf_nodes[ids] = vals
+
+    def update_batch(self, indexes, new_leaves):
+        """k x MerkleTree::update (mod.rs:690-701) for distinct leaves as one level-synchronous pass: the resulting tree is
+        the one k sequential updates produce, for height device launches instead of k * height."""
+        self._apply(*self._updated_nodes(indexes, new_leaves))
 
     def update(self, index: int, new_leaf):
         """mod.rs:690-701."""
         assert index < self.leaf_nodes.shape[0], "index out of range"
-        new_hash, path = self._updated_path(index, new_leaf)
-        self.leaf_nodes[index] = new_hash
-        cur = convert_index_to_last_level(index, self._height)
-        for _ in range(self._height - 1):
-            cur = parent(cur)
-            self.non_leaf_nodes[cur] = path.pop()
+        self.update_batch([index], np.asarray(new_leaf)[None])
 
     def check_update(self, index: int, new_leaf, asserted_new_root) -> bool:
-        """mod.rs:706-725."""
+        """mod.rs:706-725: the tree is modified only when the recomputed root equals `asserted_new_root`."""
         assert index < self.leaf_nodes.shape[0], "index out of range"
-        new_hash, path = self._updated_path(index, new_leaf)
-        if not np.array_equal(path[0], np.asarray(asserted_new_root, dtype=np.uint64)):
+        idx, new_hash, changes = self._updated_nodes([index], np.asarray(new_leaf)[None])
+        if not np.array_equal(changes[-1][1][0], np.asarray(asserted_new_root, dtype=np.uint64)):
             return False
-        self.leaf_nodes[index] = new_hash
-        cur = convert_index_to_last_level(index, self._height)
-        for _ in range(self._height - 1):
-            cur = parent(cur)
-            self.non_leaf_nodes[cur] = path.pop()
+        self._apply(idx, new_hash, changes)
+        return True
+
+    def check_update_batch(self, indexes, new_leaves, asserted_new_root) -> bool:
+        """check_update for k distinct leaves at once (same acceptance rule, one level-synchronous pass)."""
+        idx, new_hash, changes = self._updated_nodes(indexes, new_leaves)
+        if not np.array_equal(changes[-1][1][0], np.asarray(asserted_new_root, dtype=np.uint64)):
+            return False
+        self._apply(idx, new_hash, changes)
         return True

@@ -246,3 +246,84 @@ def test_tree_top_kernel_handles_every_small_shape():
         exp = np.concatenate(exp)
         got = MerkleTree.new_with_leaf_digest(cfg, cfg, d).non_leaf_nodes
         assert np.array_equal(got, exp), logn
+
+
+def test_level_synchronous_proof_and_update_batches_against_the_oracle():
+    """R/merkle_tree/mod.rs:172-212 (Path::verify), :262-331 (MultiPath::verify with its look-up table), :627-726
+    (update / check_update) as device batches -- height launches for any number of paths / leaves -- against the
+    oracle's tree and proofs."""
+    from crypto_primitives_b200.merkle_tree import MultiPath, PoseidonFieldConfig, verify_paths_batch
+    from oracle import merkle as OM
+    _, ocfg = oracle_config("jubjub_merkle_fixture")
+    cfg = product_config("jubjub_merkle_fixture")
+    f = cfg.field
+    n = 256
+    leaves = synth_elems(31, (n, 3), ocfg.p)
+    tree = MerkleTree.new(cfg, cfg, leaves)
+    O = cref.Poseidon(ocfg)
+    exp_leaf, exp_nodes = cref.poseidon_merkle(O, O, leaves, threads=8)
+    two = lambda l, r: tuple(int(x) for x in O.compress_batch(np.array([[l, r]], dtype=np.uint64))[0])   # noqa: E731
+    otree = OM.MerkleTree([tuple(int(x) for x in d) for d in exp_leaf], two, two)
+    root = tree.root()
+    # --- paths generated by the ORACLE tree, verified by the device batch (generic level-synchronous form and the one-launch kernel)
+    idxs = [0, 1, 2, 77, 128, 254, 255]
+    proofs = []
+    for i in idxs:
+        sib, path, _ = otree.generate_proof(i)
+        from crypto_primitives_b200.merkle_tree import Path
+        proofs.append(Path(np.array(sib, dtype=np.uint64), [np.array(p, dtype=np.uint64) for p in path], i))
+    ok = verify_paths_batch(cfg, cfg, root, leaves[idxs], proofs, PoseidonFieldConfig())
+    assert ok.all() and tree.verify_proofs_batch(proofs, leaves[idxs]).all()
+    bad = leaves[idxs].copy()
+    bad[3, 1, 0] ^= np.uint64(1)
+    proofs[5].auth_path[2] = proofs[5].auth_path[2].copy()
+    proofs[5].auth_path[2][0] ^= np.uint64(4)
+    ok = verify_paths_batch(cfg, cfg, root, bad, proofs, PoseidonFieldConfig())
+    assert list(ok) == [True, True, True, False, True, False, True]
+    # --- multiproof: the oracle's encoding == ours; verification hashes every tree node once per level
+    for sel in (range(n), [3, 4, 5, 200], [255]):
+        sibs, prefix, suffixes, idx = otree.generate_multi_proof(sel)
+        mp = tree.generate_multi_proof(sel)
+        assert mp.auth_paths_prefix_lenghts == prefix and mp.leaf_indexes == idx
+        assert all(np.array_equal(a, np.array(b, dtype=np.uint64)) for a, b in zip(mp.leaf_siblings_hashes, sibs))
+        assert mp.verify(cfg, cfg, root, leaves[idx])
+        assert not mp.verify(cfg, cfg, f.elements([5])[0], leaves[idx])
+        wrong = leaves[idx].copy()
+        wrong[-1, 0, 0] ^= np.uint64(1)
+        assert not mp.verify(cfg, cfg, root, wrong)
+    # --- k updates in one pass == k sequential updates == the oracle's tree of the final leaves
+    upd_idx = [0, 1, 7, 100, 101, 255]
+    new = synth_elems(32, (len(upd_idx), 3), ocfg.p)
+    seq = MerkleTree.new(cfg, cfg, leaves)
+    for k, i in enumerate(upd_idx):
+        seq.update(i, new[k])
+    tree.update_batch(upd_idx, new)
+    final = leaves.copy()
+    final[upd_idx] = new
+    exp_leaf2, exp_nodes2 = cref.poseidon_merkle(O, O, final, threads=8)
+    for t in (tree, seq):
+        assert np.array_equal(t.leaf_nodes, exp_leaf2) and np.array_equal(t.non_leaf_nodes, exp_nodes2)
+    # check_update: rejected -> untouched; accepted -> applied (single leaf and batch)
+    again = synth_elems(33, (2, 3), ocfg.p)
+    assert tree.check_update(9, again[0], root) is False and np.array_equal(tree.non_leaf_nodes, exp_nodes2)
+    final[[9, 200]] = again
+    _, exp_nodes3 = cref.poseidon_merkle(O, O, final, threads=8)
+    assert tree.check_update_batch([9, 200], again, exp_nodes3[0]) is True
+    assert np.array_equal(tree.non_leaf_nodes, exp_nodes3)
+
+
+def test_vectorised_proof_arrays_equal_generate_proof():
+    _, ocfg = oracle_config("bls_default_r2")
+    cfg = product_config("bls_default_r2")
+    for n in (2, 4, 512):
+        leaves = synth_elems(44 + n, (n, 2), ocfg.p)
+        tree = MerkleTree.new(cfg, cfg, leaves)
+        idx = sorted({0, 1, n - 1, n // 2, (n * 3) // 7})
+        sib, paths, ind = tree.generate_proofs_batch(idx)
+        for k, i in enumerate(idx):
+            p = tree.generate_proof(i)
+            assert np.array_equal(sib[k], p.leaf_sibling_hash) and int(ind[k]) == i
+            assert paths.shape[1] == len(p.auth_path) and all(np.array_equal(paths[k, j], p.auth_path[j]) for j in range(len(p.auth_path)))
+        assert tree.verify_proofs_batch((sib, paths, ind), leaves[idx]).all()
+        everything = tree.generate_proofs_batch(np.arange(n))
+        assert tree.verify_proofs_batch(everything, leaves).all()

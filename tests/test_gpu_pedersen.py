@@ -212,3 +212,41 @@ def test_ed_on_bls12_377_curve_smoke():
     assert all(curve.is_on_curve(p) for p in h) and curve.add(h[0], h[1]) == h[2]
     g00 = tuple(f.to_ints(prm.generators[0, 0]))
     assert h[0] == curve.mul(5, g00)                       # generators[0][j] = 2^j * G_0 (R/crh/pedersen/mod.rs:48-56)
+
+
+def test_byte_tree_proof_batches_and_blank():
+    """Byte-digest Config (Pedersen leaf + two-to-one, ByteDigestConverter): Path::verify for many paths, MultiPath::verify
+    and a k-leaf update as level-synchronous device batches, and MerkleTree::blank with the identity-point default digest
+    (R/merkle_tree/mod.rs:400-408) -- against the oracle."""
+    from crypto_primitives_b200.merkle_tree import verify_paths_batch
+    ow, oprm, oc, prm = setup(4, 256, 5)
+    cfg = PedersenByteConfig()
+    n = 64
+    leaves = np.ascontiguousarray(cref.synth_bytes(601, n * 32).reshape(n, 32))
+    tree = MerkleTree.new(prm, prm, leaves, config=cfg)
+    root = tree.root()
+    idx = [0, 5, 6, 31, 32, 63]
+    proofs = [tree.generate_proof(i) for i in idx]
+    assert verify_paths_batch(prm, prm, root, leaves[idx], proofs, cfg).all()
+    bad = leaves[idx].copy()
+    bad[2, 7] ^= 1
+    assert list(verify_paths_batch(prm, prm, root, bad, proofs, cfg)) == [True, True, False, True, True, True]
+    mp = tree.generate_multi_proof(range(n))
+    assert mp.verify(prm, prm, root, leaves, config=cfg)
+    bad_all = leaves.copy()
+    bad_all[40, 0] ^= 1
+    assert not mp.verify(prm, prm, root, bad_all, config=cfg)
+    new = np.ascontiguousarray(cref.synth_bytes(602, 3 * 32).reshape(3, 32))
+    tree.update_batch([1, 2, 50], new)
+    leaves[[1, 2, 50]] = new
+    exp_leaf, exp_nodes = cref.pedersen_merkle(oc, oc, leaves, threads=8)
+    assert np.array_equal(tree.leaf_nodes, exp_leaf) and np.array_equal(tree.non_leaf_nodes, exp_nodes)
+    # blank: every leaf digest = the identity point (0, 1); inner levels from the oracle's compress
+    blank = MerkleTree.blank(prm, prm, 4, config=cfg)
+    assert blank.leaf_nodes.shape == (8, 2, 4)
+    ident = np.broadcast_to(cp.BLS12_381_FR.elements([0, 1]).reshape(1, 2, 4), (8, 2, 4))
+    lvl = oc.compress_batch(np.ascontiguousarray(ident).reshape(4, 2, 2, 4), threads=2)
+    assert np.array_equal(blank.non_leaf_nodes[3:7], lvl)
+    lvl = oc.compress_batch(lvl.reshape(2, 2, 2, 4), threads=2)
+    assert np.array_equal(blank.non_leaf_nodes[1:3], lvl)
+    assert np.array_equal(blank.root(), oc.compress_batch(lvl.reshape(1, 2, 2, 4))[0])
