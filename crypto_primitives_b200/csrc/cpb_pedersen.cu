@@ -59,15 +59,57 @@ k_pedersen_table(const u32* __restrict__ consts, const u32* __restrict__ gens_xy
         te_niels<F>(yp, ym, t2d, x, y, d2, pm);
         te_madd<F>(acc, yp, ym, t2d, pm);
     }
-    u32 zi[8], x[8], y[8], yp[8], ym[8], t2d[8];
-    fp_inv<F>(zi, acc.Z, pm);
-    fp_mul<F>(x, acc.X, zi, pm);
-    fp_mul<F>(y, acc.Y, zi, pm);
-    te_niels<F>(yp, ym, t2d, x, y, d2, pm);
+    // projective (X, Y, Z) into the entry's 96 bytes; k_pedersen_table_finish normalises in place
     u32* o = table + e * kEntryWords;
-    st_elem(o, yp);
-    st_elem(o + 8, ym);
-    st_elem(o + 16, t2d);
+    st_elem(o, acc.X);
+    st_elem(o + 8, acc.Y);
+    st_elem(o + 16, acc.Z);
+}
+
+// Second pass of the table build: entries (X, Y, Z) -> affine-Niels (y+x, y-x, 2d*x*y), with ONE field inversion per
+// kFinishBatch entries (Montgomery's trick along the thread's own sequence of entries; prefix products in local memory).
+// The first version inverted per entry: 4.2 M Fermat inversions (~380 products each) for the 16-bit tables of a 4x256 window.
+constexpr int kFinishBatch = 16;
+template <class F>
+__global__ void __launch_bounds__(128)
+k_pedersen_table_finish(const u32* __restrict__ consts, u32* __restrict__ table, long n_entries, int zero) {
+    const long stride = (n_entries + kFinishBatch - 1) / kFinishBatch;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= stride) return;
+    const u32* ct = consts + (int)threadIdx.x * zero;
+    u32 pm[8], d2[8], acc[8], z[8];
+    ld_elem(pm, ct);
+    ld_elem(d2, ct + 8);
+    u32 pref[kFinishBatch][8];
+    fp_one<F>(acc);
+#pragma unroll 1
+    for (int j = 0; j < kFinishBatch; j++) {
+        const long i = t + j * stride;
+        if (i >= n_entries) break;
+        fp_copy(pref[j], acc);
+        ld_elem(z, table + i * kEntryWords + 16);
+        fp_mul<F>(acc, acc, z, pm);                        // Z != 0: the addition law is complete
+    }
+    u32 inv[8];
+    fp_inv<F>(inv, acc, pm);
+#pragma unroll 1
+    for (int j = kFinishBatch - 1; j >= 0; j--) {
+        const long i = t + j * stride;
+        if (i >= n_entries) continue;
+        u32* o = table + i * kEntryWords;
+        u32 zi[8], x[8], y[8], yp[8], ym[8], t2d[8];
+        fp_mul<F>(zi, inv, pref[j], pm);                   // 1 / Z_i
+        ld_elem(z, o + 16);
+        fp_mul<F>(inv, inv, z, pm);
+        ld_elem(x, o);
+        ld_elem(y, o + 8);
+        fp_mul<F>(x, x, zi, pm);
+        fp_mul<F>(y, y, zi, pm);
+        te_niels<F>(yp, ym, t2d, x, y, d2, pm);
+        st_elem(o, yp);
+        st_elem(o + 8, ym);
+        st_elem(o + 16, t2d);
+    }
 }
 
 // 16 input bytes starting at `off` of a `len`-byte message (zero beyond len), as 4 LE words.
@@ -196,8 +238,8 @@ k_pedersen_hash_gather(PedersenDev P, const u32* __restrict__ consts, const u32*
     const int total = P.n_in_chunks + (rand32 ? P.n_rand_chunks : 0);
     TePoint acc;
     te_identity<F>(acc);
-#pragma unroll 1
-    for (int c = 0; c < total; c++) {
+    // table entry of lookup c for this message (the lookup value comes from up to 3 input bytes)
+    auto entry = [&](int c) -> const uint4* {
         const bool is_rand = c >= P.n_in_chunks;
         const uint8_t* src = is_rand ? rnd : msg;
         const long slen = is_rand ? 32 : len;
@@ -208,13 +250,30 @@ k_pedersen_hash_gather(PedersenDev P, const u32* __restrict__ consts, const u32*
         for (int k = 0; k < 3; k++)
             if (byte + k < slen) v |= (u32)__ldg(src + byte + k) << (8 * k);
         v = (v >> (bit & 7)) & vmask;
-        const u32* e = table + (((long)c << cb) + v) * kEntryWords;
+        return reinterpret_cast<const uint4*>(table + (((long)c << cb) + v) * kEntryWords);
+    };
+    // Software pipeline over the gathers: the entry of lookup c+1 is loaded into registers and the entry of lookup
+    // c+kPrefetchAhead is pulled into L2 while the mixed addition of lookup c (7 field products) runs, so the
+    // ~1 us DRAM latency of a 96-byte random access is off the critical path (ncu round 1: long_scoreboard 0.87 / issue).
+    constexpr int kPrefetchAhead = 4;
+    uint4 q0, q1, q2, q3, q4, q5;
+    if (total > 0) {
+        const uint4* e4 = entry(0);
+        q0 = __ldg(e4); q1 = __ldg(e4 + 1); q2 = __ldg(e4 + 2); q3 = __ldg(e4 + 3); q4 = __ldg(e4 + 4); q5 = __ldg(e4 + 5);
+    }
+#pragma unroll 1
+    for (int c = 1; c < kPrefetchAhead && c < total; c++) asm volatile("prefetch.global.L2 [%0];" ::"l"(entry(c)));
+#pragma unroll 1
+    for (int c = 0; c < total; c++) {
         u32 yp[8], ym[8], t2d[8];
-        const uint4* e4 = reinterpret_cast<const uint4*>(e);
-        uint4 q0 = __ldg(e4), q1 = __ldg(e4 + 1), q2 = __ldg(e4 + 2), q3 = __ldg(e4 + 3), q4 = __ldg(e4 + 4), q5 = __ldg(e4 + 5);
         yp[0] = q0.x; yp[1] = q0.y; yp[2] = q0.z; yp[3] = q0.w; yp[4] = q1.x; yp[5] = q1.y; yp[6] = q1.z; yp[7] = q1.w;
         ym[0] = q2.x; ym[1] = q2.y; ym[2] = q2.z; ym[3] = q2.w; ym[4] = q3.x; ym[5] = q3.y; ym[6] = q3.z; ym[7] = q3.w;
         t2d[0] = q4.x; t2d[1] = q4.y; t2d[2] = q4.z; t2d[3] = q4.w; t2d[4] = q5.x; t2d[5] = q5.y; t2d[6] = q5.z; t2d[7] = q5.w;
+        if (c + kPrefetchAhead < total) asm volatile("prefetch.global.L2 [%0];" ::"l"(entry(c + kPrefetchAhead)));
+        if (c + 1 < total) {
+            const uint4* e4 = entry(c + 1);
+            q0 = __ldg(e4); q1 = __ldg(e4 + 1); q2 = __ldg(e4 + 2); q3 = __ldg(e4 + 3); q4 = __ldg(e4 + 4); q5 = __ldg(e4 + 5);
+        }
         te_madd<F>(acc, yp, ym, t2d, pm);
     }
     u32* o = out + 32 * i;
@@ -672,10 +731,15 @@ cpb_status cpb_pedersen_ctx_create_ex(int curve_id, int window_size, int num_win
             if (n_chunks <= 0) return;
             long entries = (long)n_chunks << chunk_bits;
             int grid = (int)((entries + 255) / 256);
-            if (c->field_id == CPB_BLS12_381_FR)
+            long fin_threads = (entries + kFinishBatch - 1) / kFinishBatch;
+            int fgrid = (int)((fin_threads + 127) / 128);
+            if (c->field_id == CPB_BLS12_381_FR) {
                 k_pedersen_table<Bls12_381_Fr><<<grid, 256>>>(c->d_consts, gens, n_gens, n_chunks, chunk_bits, table, 0);
-            else
+                k_pedersen_table_finish<Bls12_381_Fr><<<fgrid, 128>>>(c->d_consts, table, entries, 0);
+            } else {
                 k_pedersen_table<Bls12_377_Fr><<<grid, 256>>>(c->d_consts, gens, n_gens, n_chunks, chunk_bits, table, 0);
+                k_pedersen_table_finish<Bls12_377_Fr><<<fgrid, 128>>>(c->d_consts, table, entries, 0);
+            }
         };
         build(d_gens, (int)settable, c->dev.n_in_chunks, c->d_table);
         build(d_rgens, (int)n_rand, c->dev.n_rand_chunks, c->d_table + (size_t)c->dev.n_in_chunks * chunk_words);

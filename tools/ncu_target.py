@@ -1,4 +1,4 @@
-"""Short workload for ncu captures.  usage: ncu_target.py [bls|bn254] [compress|merkle|pedersen|pedersen8]"""
+"""Short workload for ncu captures.  usage: ncu_target.py [bls|bn254] [compress|merkle|top|pedersen|pedersen8] [log2 n]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -35,7 +35,13 @@ if what in ("pedersen", "pedersen8"):
         N.check(N.lib.cpb_pedersen_crh_batch_dev(ctx, inp.data_ptr(), 128, 128, out.data_ptr(), n, st))
 else:
     x = torch.randint(0, 2**59, (n, 2, 4), dtype=torch.int64).to(dev)
-    if what == "merkle":
+    if what == "top":                               # the tree-top kernel: every level of a 2^logn-digest tree in one launch
+        d = x[:, 0, :].contiguous()
+        nn = torch.empty((n - 1, 4), dtype=torch.int64, device=dev)
+        ctx = cfg.context(0)
+        for _ in range(3):
+            N.check(N.lib.cpb_merkle_poseidon_from_digests_dev(ctx, d.data_ptr(), n, nn.data_ptr(), st))
+    elif what == "merkle":
         ln = torch.empty((n, 4), dtype=torch.int64, device=dev)
         nn = torch.empty((n - 1, 4), dtype=torch.int64, device=dev)
         ctx = cfg.context(0)
