@@ -245,11 +245,11 @@ k_pedersen_hash_gather(PedersenDev P, const u32* __restrict__ consts, const u32*
         const long slen = is_rand ? 32 : len;
         const long bit = (long)(is_rand ? c - P.n_in_chunks : c) * cb;
         const long byte = bit >> 3;
-        u32 v = 0;
+        u64 v64 = 0;
 #pragma unroll
-        for (int k = 0; k < 3; k++)
-            if (byte + k < slen) v |= (u32)__ldg(src + byte + k) << (8 * k);
-        v = (v >> (bit & 7)) & vmask;
+        for (int k = 0; k < 4; k++)                      // chunk_bits + 7 <= 29 bits: four bytes always cover a lookup value
+            if (byte + k < slen) v64 |= (u64)__ldg(src + byte + k) << (8 * k);
+        const u32 v = (u32)(v64 >> (bit & 7)) & vmask;
         return reinterpret_cast<const uint4*>(table + (((long)c << cb) + v) * kEntryWords);
     };
     // Software pipeline over the gathers: the entry of lookup c+1 is loaded into registers and the entry of lookup
@@ -662,16 +662,18 @@ cpb_status cpb_pedersen_ctx_create_ex(int curve_id, int window_size, int num_win
     return cpb::guarded([&]() -> cpb_status {
     if (!out) return fail(CPB_NULL_POINTER, "null out");
     if (chunk_bits == 0) {
-        // default: the widest lookup whose tables stay under 1 GiB (16 bits: 0.5 GB for a 1024-bit input + 252
-        // randomness generators; measured 1.9x the 8-bit shared-memory path), else 12 (L2-resident), else 8
+        // default: the widest lookup whose tables stay under 2 GiB -- 18 bits for a 1024-bit input + 252 randomness
+        // generators (1.8 GB; one gathered 96-byte entry and one mixed addition per 18 input bits; measured on a B200,
+        // 2^20 x 128-byte inputs: 8 bits 67, 12 bits 96, 16 bits 126, 18 bits 140, 20 bits 152, 22 bits 166 M hashes/s --
+        // HBM capacity traded for integer-pipe work), else 16, else 12 (L2-resident), else 8 (shared memory)
         const size_t bits_total = (size_t)window_size * num_windows + n_rand;
         chunk_bits = kDefaultChunkBits;
-        for (int cand : {16, 12}) {
+        for (int cand : {18, 16, 12}) {
             size_t chunks = (bits_total + cand - 1) / cand + 1;
-            if (chunks * (((size_t)kEntryWords * 4) << cand) <= ((size_t)1 << 30)) { chunk_bits = cand; break; }
+            if (chunks * (((size_t)kEntryWords * 4) << cand) <= ((size_t)2 << 30)) { chunk_bits = cand; break; }
         }
     }
-    if (chunk_bits < 8 || chunk_bits > 16) return fail(CPB_BAD_PARAMS, "chunk_bits must be 8..16 (0 = default)");
+    if (chunk_bits < 8 || chunk_bits > 22) return fail(CPB_BAD_PARAMS, "chunk_bits must be 8..22 (0 = default)");
     *out = nullptr;
     CurveInfo ci;
     if (!curve_info(curve_id, ci)) return fail(CPB_BAD_PARAMS, "unknown curve id %d", curve_id);

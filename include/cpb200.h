@@ -192,8 +192,9 @@ cpb_status cpb_pedersen_ctx_create(int curve_id, int window_size, int num_window
                                    size_t n_rand, const uint64_t* rand_generators_xy, int device,
                                    cpb_pedersen_ctx** out);
 /* Same, choosing how many consecutive input bits one table lookup covers: 8 = 24 KB tables per chunk streamed through
- * shared memory by TMA; 9..16 = larger L2/HBM-resident tables gathered per lookup (fewer additions per hash, results
- * identical); 0 = library default. */
+ * shared memory by TMA; 9..22 = larger L2/HBM-resident tables gathered per lookup (fewer additions per hash, results
+ * identical; table bytes = ceil(bits / chunk_bits) * 96 * 2^chunk_bits: 0.4 GB at 16, 5.2 GB at 20 for a 1024-bit
+ * input); 0 = library default (the widest of 18 / 16 / 12 / 8 whose tables stay under 2 GiB). */
 cpb_status cpb_pedersen_ctx_create_ex(int curve_id, int window_size, int num_windows, const uint64_t* generators_xy,
                                       size_t n_rand, const uint64_t* rand_generators_xy, int device, int chunk_bits,
                                       cpb_pedersen_ctx** out);

@@ -289,8 +289,15 @@ def test_level_synchronous_proof_and_update_batches_against_the_oracle():
         assert mp.verify(cfg, cfg, root, leaves[idx])
         assert not mp.verify(cfg, cfg, f.elements([5])[0], leaves[idx])
         wrong = leaves[idx].copy()
-        wrong[-1, 0, 0] ^= np.uint64(1)
+        wrong[0, 0, 0] ^= np.uint64(1)
         assert not mp.verify(cfg, cfg, root, wrong)
+    # Faithful to the reference's look-up table (mod.rs:304-306, `hash_lut.entry(..).or_insert_with(..)`): when both leaves of a
+    # pair are in the multiproof, their parent is hashed from the FIRST one's (leaf, sibling hash) and the second leaf's
+    # claimed hash is never used -- a tampered second leaf passes there, and therefore here.
+    mp = tree.generate_multi_proof(range(n))
+    second = leaves.copy()
+    second[255, 0, 0] ^= np.uint64(1)
+    assert mp.verify(cfg, cfg, root, second)
     # --- k updates in one pass == k sequential updates == the oracle's tree of the final leaves
     upd_idx = [0, 1, 7, 100, 101, 255]
     new = synth_elems(32, (len(upd_idx), 3), ocfg.p)

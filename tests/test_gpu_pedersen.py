@@ -52,7 +52,7 @@ def test_crh_matches_oracle(ws, nw, lens):
     assert tuple(cp.BLS12_381_FR.to_ints(CRH.evaluate(prm, one))) == OPD.crh_evaluate(oprm, ow, one)
 
 
-@pytest.mark.parametrize("chunk_bits", [9, 12, 16])
+@pytest.mark.parametrize("chunk_bits", [9, 12, 16, 17, 19, 21])
 @pytest.mark.parametrize("ws,nw,ln", [(4, 256, 128), (4, 256, 33), (127, 9, 142), (4, 9, 4)])
 def test_wide_table_chunks_give_identical_results(chunk_bits, ws, nw, ln):
     """cpb_pedersen_ctx_create_ex: 9..16 input bits per table lookup (L2/HBM-resident tables, gathered) instead of 8

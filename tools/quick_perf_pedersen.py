@@ -29,7 +29,7 @@ from crypto_primitives_b200.crh.pedersen import Parameters
 base = Commitment.setup(Rng(1), Window(4, 256))
 dev = torch.device("cuda:0")
 st = torch.cuda.current_stream().cuda_stream
-for cb in (8, 12, 16):
+for cb in tuple(int(x) for x in sys.argv[1].split(",")) if len(sys.argv) > 1 else (8, 12, 16):
   prm = Parameters(base.curve, base.window, base.generators, base.randomness_generator, chunk_bits=cb)
   t0 = time.time(); ctx = prm.context(0); print(f"chunk_bits={cb}: context (table build) {time.time() - t0:.3f} s", flush=True)
   for logn in (20,):
