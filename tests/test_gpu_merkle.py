@@ -294,10 +294,16 @@ def test_level_synchronous_proof_and_update_batches_against_the_oracle():
     # Faithful to the reference's look-up table (mod.rs:304-306, `hash_lut.entry(..).or_insert_with(..)`): when both leaves of a
     # pair are in the multiproof, their parent is hashed from the FIRST one's (leaf, sibling hash) and the second leaf's
     # claimed hash is never used -- a tampered second leaf passes there, and therefore here.
+    # The same table shadows whole subtrees: a later path stops being checked at its first ancestor that an earlier path
+    # already inserted (from that path's own, correct, auth-path sibling).  Bug-compatible on purpose: same boolean as
+    # the reference for every input.
     mp = tree.generate_multi_proof(range(n))
     second = leaves.copy()
     second[255, 0, 0] ^= np.uint64(1)
     assert mp.verify(cfg, cfg, root, second)
+    shadowed = leaves.copy()
+    shadowed[40, 0, 0] ^= np.uint64(1)                 # leaf 40: its ancestor at depth 2 was inserted by path 32
+    assert mp.verify(cfg, cfg, root, shadowed)
     # --- k updates in one pass == k sequential updates == the oracle's tree of the final leaves
     upd_idx = [0, 1, 7, 100, 101, 255]
     new = synth_elems(32, (len(upd_idx), 3), ocfg.p)

