@@ -90,3 +90,35 @@ def verify_path(proof, leaf_digest, root, bottom_two_to_one, compress) -> bool:
         cur = compress(l, r)
         index >>= 1
     return cur == root
+
+
+def verify_multi_path(multi_proof, leaf_digests, root, bottom_two_to_one, compress) -> bool:
+    """MultiPath::verify :262-331, sequential, with the reference's look-up table of already hashed nodes
+    (`hash_lut.entry(index_in_tree).or_insert_with(..)`, :304-306 and :316-318): a node is hashed by the FIRST path that
+    reaches it; later paths take the table's value and never compare their own (left, right) with it.
+    multi_proof = (leaf_siblings_hashes, prefix_lengths, suffixes, leaf_indexes); leaf_digests already hashed."""
+    sibs, prefix, suffixes, idx = multi_proof
+    height = len(suffixes[0]) + 2                          # :269
+    lut = {}
+    prev = list(suffixes[0])                               # :277
+    for i, leaf_index in enumerate(idx):
+        k = prefix[i]
+        auth = list(suffixes[i]) if k == 0 else prev[:k] + list(suffixes[i])    # prefix_decode_path :284-288
+        prev = auth
+        claimed, sib = leaf_digests[i], sibs[i]
+        l, r = (claimed, sib) if leaf_index & 1 == 0 else (sib, claimed)
+        index = leaf_index >> 1
+        in_tree = parent(leaf_index + (1 << (height - 1)) - 1)
+        if in_tree not in lut:
+            lut[in_tree] = bottom_two_to_one(l, r)
+        cur = lut[in_tree]
+        for level in range(len(auth) - 1, -1, -1):
+            l, r = (cur, auth[level]) if index & 1 == 0 else (auth[level], cur)
+            index >>= 1
+            in_tree = parent(in_tree)
+            if in_tree not in lut:
+                lut[in_tree] = compress(l, r)
+            cur = lut[in_tree]
+        if cur != root:                                     # :321-323
+            return False
+    return True
