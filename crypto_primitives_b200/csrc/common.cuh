@@ -64,6 +64,10 @@ struct DeviceGuard {
 // Number of SMs of a device (cached per device id).
 int sm_count(int device);
 
+// Stream-ordered scratch (cudaMallocAsync) is used per call; by default the driver's pool returns memory to the OS at
+// every synchronisation, which makes the next cudaMallocAsync re-map (and serialise) each time: keep it cached in the pool.
+void keep_pool_memory(int device);
+
 // Grow-only device scratch buffer owned by a context (guarded by the context mutex).
 struct Scratch {
     void* ptr = nullptr;

@@ -515,18 +515,6 @@ extern "C" int cpb_poseidon_ctx_device(const cpb_poseidon_ctx* ctx);
 namespace {
 
 
-// The hash launchers take their projective scratch from the device's stream-ordered pool.  By default that pool
-// returns memory to the OS at every synchronisation, which makes the next cudaMallocAsync re-map 128 B x n each call;
-// keep the memory cached in the pool instead.
-void keep_pool_memory(int device) {
-    cudaMemPool_t pool = nullptr;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    cudaGetLastError();
-}
-
 struct CurveInfo {
     int field_id;
     bool d_is_ratio;      // d = -(num/den) when true, else d = num

@@ -31,6 +31,14 @@ cpb_status fail(cpb_status st, const char* fmt, ...) {
     last_error_ref() = buf;
     return st;
 }
+void keep_pool_memory(int device) {
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+}
 int sm_count(int device) {
     static int cache[64];
     static std::mutex mu;
@@ -184,7 +192,7 @@ cpb_status check_ctx(const cpb_poseidon_ctx* c) {
 // 2^l nodes at [2^l - 1, 2^(l+1) - 1); subtree k owns the k-th 1/S of every level l >= log2 S
 // (new_with_leaf_digest, R/merkle_tree/mod.rs:424-523).  S = 1, k = 0 is the whole tree.
 cpb_status merkle_subtree_levels(cpb_poseidon_ctx* node, const u32* leaf_digests, size_t n, u32* nodes, size_t S, size_t k,
-                                 cudaStream_t st, const MerkleHost* H, const ExchangeDev* X) {
+                                 cudaStream_t st, const MerkleHost* H, const ExchangeDev* X, int* small_from) {
     int h = 0;
     while (((size_t)1 << h) < n) h++;
     int lg = 0;
@@ -199,7 +207,8 @@ cpb_status merkle_subtree_levels(cpb_poseidon_ctx* node, const u32* leaf_digests
             J.leaf_digests = leaf_digests; J.nodes = nodes; J.h = h; J.lgS = lg; J.k = (long)k; J.l_start = l; J.l_end = lg;
             if (X && S == 1) J.x = *X;
             CPB_TRY(launch_tree_top(node, J, st));
-            if (H)
+            if (small_from) *small_from = l;                // the caller copies levels <= l out (all subtrees at once)
+            else if (H)
                 for (int q = l; q >= lg; q--) {
                     size_t c2 = ((size_t)1 << q) / S, off = (((size_t)1 << q) - 1) + k * c2;
                     CPB_CUDA(cudaMemcpyAsync(H->node_ptr(q, k * c2), nodes + 8 * off, c2 * 32, cudaMemcpyDeviceToHost, st));
@@ -256,6 +265,7 @@ cpb_status merkle_build_streams(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, 
         return CPB_OK;
     }
     CPB_TRY(ensure_side_streams(node, S));
+    int small_from = -1;                 // first (largest) level the subtrees' tree-top launches covered, when they ran
     cudaEvent_t start = nullptr, done[8] = {};
     CPB_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
     cudaError_t e = cudaEventRecord(start, st);
@@ -273,7 +283,7 @@ cpb_status merkle_build_streams(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, 
         if (rc == CPB_OK && H)
             e = cudaMemcpyAsync(H->leaf_nodes + 8 * (k * per), leaf_nodes + 8 * (k * per), per * 32, cudaMemcpyDeviceToHost, sk);
         if (e != cudaSuccess) break;
-        if (rc == CPB_OK) rc = merkle_subtree_levels(node, leaf_nodes, n, nodes, S, k, sk, H);
+        if (rc == CPB_OK) rc = merkle_subtree_levels(node, leaf_nodes, n, nodes, S, k, sk, H, nullptr, H ? &small_from : nullptr);
         if (rc != CPB_OK) break;
         e = cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventRecord(done[k], sk);
@@ -300,9 +310,17 @@ cpb_status merkle_build_streams(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, 
             CPB_TRY(launch_crh(node, nodes + 8 * ((((size_t)1 << (l + 1)) - 1)), 2, nodes + 8 * (cnt - 1), cnt, st));
         }
     }
-    if (H)
-        for (int l = lg - 1; l >= 0; l--)
-            CPB_CUDA(cudaMemcpyAsync(H->node_ptr(l, 0), nodes + 8 * (((size_t)1 << l) - 1), ((size_t)1 << l) * 32, cudaMemcpyDeviceToHost, st));
+    if (H) {
+        // levels 0 .. small_from (the replicated top and, when the tree-top kernel ran, every small level of all the
+        // subtrees): a contiguous prefix of the heap-ordered array -- one copy, or one per level for a shard (g > 0)
+        const int last = small_from >= 0 ? small_from : lg - 1;
+        if (H->g == 0) {
+            CPB_CUDA(cudaMemcpyAsync(H->nodes, nodes, (((size_t)2 << last) - 1) * 32, cudaMemcpyDeviceToHost, st));
+        } else {
+            for (int l = last; l >= 0; l--)
+                CPB_CUDA(cudaMemcpyAsync(H->node_ptr(l, 0), nodes + 8 * (((size_t)1 << l) - 1), ((size_t)1 << l) * 32, cudaMemcpyDeviceToHost, st));
+        }
+    }
     return CPB_OK;
 }
 
@@ -511,6 +529,7 @@ cpb_status cpb_poseidon_ctx_create(int field_id, int rate, int capacity, int ful
     CPB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
     if (major != 10) return fail(CPB_NO_DEVICE, "device %d is sm_%d0; this library is built for sm_100a only", device, major);
 
+    keep_pool_memory(device);          // the tree-top launches take their progress words from the stream-ordered pool
     cpb_poseidon_ctx* c = new cpb_poseidon_ctx();
     c->field_id = field_id;
     c->device = device;

@@ -367,7 +367,7 @@ cpb_status check_ctx(const cpb_poseidon_ctx* c);
 bool pow2_gt1(size_t n);
 cpb_status launch_crh(cpb_poseidon_ctx* c, const u32* in, size_t len, u32* out, size_t n, cudaStream_t st, size_t n_out = 1);
 cpb_status merkle_subtree_levels(cpb_poseidon_ctx* node, const u32* leaf_digests, size_t n, u32* nodes, size_t S, size_t k,
-                                 cudaStream_t st, const MerkleHost* H = nullptr, const ExchangeDev* X = nullptr);
+                                 cudaStream_t st, const MerkleHost* H = nullptr, const ExchangeDev* X = nullptr, int* small_from = nullptr);
 cpb_status merkle_build_streams(cpb_poseidon_ctx* leaf, cpb_poseidon_ctx* node, const u32* leaves, size_t leaf_len, size_t n,
                                 u32* leaf_nodes, u32* nodes, cudaStream_t st, const MerkleHost* H = nullptr,
                                 const ExchangeDev* X = nullptr);
