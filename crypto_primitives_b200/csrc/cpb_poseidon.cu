@@ -138,6 +138,16 @@ size_t team_max() {
     }
     return (size_t)v;
 }
+// Hand-over point of a subtree to the tree-top kernel when S subtrees are built concurrently: the four-warp kernel spends
+// ~1.4x the multiplications of the one-hash-per-thread kernel to halve the dependent chain, which pays only once the GPU is
+// latency-bound -- about 8192 hashes in flight over all streams (measured, profiles/r2_exp_team_max.txt: 2^21-leaf BN254
+// tree, overhead over the bulk rate 2.9 / 2.3 / 1.9 / 2.0 ms for per-subtree limits 4096 / 2048 / 1024 / 256 at S = 8).
+// CPB_TEAM_MAX, when set, is the per-subtree limit as given.
+size_t team_max_for(size_t S) {
+    if (getenv("CPB_TEAM_MAX")) return team_max();
+    size_t v = 8192 / (S ? S : 1);
+    return v < team_max() ? v : team_max();
+}
 bool team_capable(const cpb_poseidon_ctx* c) { return c->dev.t == 3 && c->dev.cap == 1 && c->dev.alpha >= 2; }
 
 cpb_status launch_tree_top(cpb_poseidon_ctx* c, const TopJob& J, cudaStream_t st) {
@@ -198,9 +208,10 @@ cpb_status merkle_subtree_levels(cpb_poseidon_ctx* node, const u32* leaf_digests
     int lg = 0;
     while (((size_t)1 << lg) < S) lg++;
     const bool team = team_capable(node) && team_max() > 0;
+    const size_t tmax = team_max_for(S);
     for (int l = h - 1; l >= lg; l--) {
         size_t cnt = ((size_t)1 << l) / S;
-        if (team && cnt <= team_max()) {
+        if (team && cnt <= tmax) {
             // every remaining level of this subtree in ONE launch (k_poseidon_tree_top), optionally with the multi-GPU
             // root exchange and the replicated top levels fused in (X: only for the whole local tree, S == 1)
             TopJob J;
@@ -335,7 +346,7 @@ size_t count_launches(const cpb_poseidon_ctx* node, size_t n) {
     size_t per_subtree = 1;                                   // the leaf hash
     for (int l = h - 1; l >= lg; l--) {
         size_t cnt = ((size_t)1 << l) / S;
-        if (team && cnt <= team_max()) { per_subtree += 1; break; }
+        if (team && cnt <= team_max_for(S)) { per_subtree += 1; break; }
         per_subtree += 1;
     }
     size_t top = S > 1 ? (team ? 1 : (size_t)lg) : 0;
