@@ -27,11 +27,28 @@ extern "C" {
     fn cpb_poseidon_compress_batch(ctx: *mut cpb_poseidon_ctx, pairs: *const u64, out: *mut u64, n: usize) -> c_int;
     fn cpb_merkle_poseidon_build(leaf: *mut cpb_poseidon_ctx, node: *mut cpb_poseidon_ctx, leaves: *const u64, leaf_len: usize,
                                  n: usize, leaf_nodes: *mut u64, non_leaf_nodes: *mut u64) -> c_int;
+    // page-lock a `Vec<Fr>`'s storage once so the host-pointer calls copy at full PCIe rate (ABI v3)
+    fn cpb_host_register(ptr: *mut core::ffi::c_void, bytes: usize) -> c_int;
+    fn cpb_host_unregister(ptr: *mut core::ffi::c_void) -> c_int;
+    // one process, several GPUs (ABI v3): peer-memory root exchange fused into the last kernel, or ncclCommInitAll + ncclAllGather
+    fn cpb_multi_create(ndev: c_int, devices: *const c_int, out: *mut *mut cpb_multi) -> c_int;
+    fn cpb_multi_destroy(m: *mut cpb_multi);
+    fn cpb_multi_uses_nccl(m: *const cpb_multi) -> c_int;
+    fn cpb_merkle_poseidon_build_multi(m: *mut cpb_multi, leaf_ctxs: *const *mut cpb_poseidon_ctx, node_ctxs: *const *mut cpb_poseidon_ctx,
+                                       leaves: *const u64, leaf_len: usize, n: usize, leaf_nodes: *mut u64, non_leaf_nodes: *mut u64) -> c_int;
+}
+
+#[allow(non_camel_case_types)]
+#[repr(C)]
+pub struct cpb_multi {
+    _private: [u8; 0],
 }
 
 const CPB_OK: c_int = 0;
 const CPB_BAD_LENGTH: c_int = 1;
 const CPB_NOT_POW2: c_int = 3;
+#[allow(dead_code)]
+const CPB_NCCL_ERROR: c_int = 9;      // surfaces as Err(CpbError(9, ..)) through `check`
 
 #[derive(Debug)]
 pub struct CpbError(pub c_int, pub String);
@@ -181,6 +198,44 @@ impl<F: GpuField> GpuMerkleTree<F> {
         path.reverse();
         path
     }
+}
+
+/// `MerkleTree::new` (R/merkle_tree/mod.rs:411-422) on ALL the GPUs of a group driven by this process: the leaves are sharded
+/// contiguously over the devices, every device builds its subtree, the subtree roots are exchanged once (inside the last
+/// kernel over NVLink peer memory, or by one `ncclAllGather`) and the result is the reference's two arrays, exactly as from
+/// one GPU.  `params[d]` are contexts of the SAME `PoseidonConfig` created on `devices[d]`.
+pub struct GpuGroup {
+    raw: *mut cpb_multi,
+    ndev: usize,
+}
+unsafe impl Send for GpuGroup {}
+unsafe impl Sync for GpuGroup {}
+impl GpuGroup {
+    pub fn new(devices: &[i32]) -> Result<Self, Error> {
+        let mut raw = core::ptr::null_mut();
+        check(unsafe { cpb_multi_create(devices.len() as c_int, devices.as_ptr(), &mut raw) })?;
+        Ok(Self { raw, ndev: devices.len() })
+    }
+    pub fn uses_nccl(&self) -> bool { unsafe { cpb_multi_uses_nccl(self.raw) != 0 } }
+    pub fn merkle_tree<F: GpuField>(&self, leaf: &[GpuPoseidonParams<F>], two_to_one: &[GpuPoseidonParams<F>], leaves: &[Vec<F>])
+        -> Result<GpuMerkleTree<F>, Error> {
+        assert!(leaf.len() == self.ndev && two_to_one.len() == self.ndev, "one context per device");
+        let n = leaves.len();
+        let leaf_len = leaves.first().map_or(0, |l| l.len());
+        let mut flat: Vec<u64> = leaves.iter().flat_map(|l| flatten(l)).collect();
+        let (mut ln, mut nn) = (vec![0u64; 4 * n], vec![0u64; 4 * n.saturating_sub(1)]);
+        let lc: Vec<*mut cpb_poseidon_ctx> = leaf.iter().map(|p| p.ctx.0).collect();
+        let nc: Vec<*mut cpb_poseidon_ctx> = two_to_one.iter().map(|p| p.ctx.0).collect();
+        // optional: pin the big buffers for the duration of the call (pageable memory works, at about half the PCIe rate)
+        unsafe { cpb_host_register(flat.as_mut_ptr() as *mut _, flat.len() * 8) };
+        let st = unsafe { cpb_merkle_poseidon_build_multi(self.raw, lc.as_ptr(), nc.as_ptr(), flat.as_ptr(), leaf_len, n, ln.as_mut_ptr(), nn.as_mut_ptr()) };
+        unsafe { cpb_host_unregister(flat.as_mut_ptr() as *mut _) };
+        check(st)?;
+        Ok(GpuMerkleTree { leaf_nodes: unflatten(&ln), non_leaf_nodes: unflatten(&nn), height: n.trailing_zeros() as usize + 1 })
+    }
+}
+impl Drop for GpuGroup {
+    fn drop(&mut self) { unsafe { cpb_multi_destroy(self.raw) } }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
