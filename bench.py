@@ -279,7 +279,16 @@ def run_b200(args):
     # N > 1: the subtree roots are exchanged inside the last kernel of each rank's build over NVLink peer memory (CUDA IPC);
     # CPB_BENCH_EXCHANGE=nccl selects the torch.distributed all-gather for the headline instead (timed alongside anyway)
     use_fused = world > 1 and os.environ.get("CPB_BENCH_EXCHANGE", "fused") != "nccl"
-    ex = Exchange(local_rank) if world > 1 else None
+    ex, ex_error = None, None
+    if world > 1:
+        try:
+            ex = Exchange(local_rank)
+        except Exception as e:                          # e.g. CUDA IPC not permitted in this container: every rank falls back together
+            ex_error = repr(e)
+        ok = torch.tensor([0 if ex is None else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not bool(ok.item()):
+            ex, use_fused = None, False
     # this rank's slice of the global leaf stream: leaves [rank*n_local, (rank+1)*n_local)
     leaves = BI.field_elements_torch(torch, N, fid, seed, rank * n_local * leaf_len, n_local * leaf_len, local_rank).view(n_local, leaf_len, 4)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
@@ -330,7 +339,7 @@ def run_b200(args):
 
     # ---- N > 1: the other root exchange (NCCL all-gather issued from Python <-> fused peer-memory kernel), 3 steps
     other_ms = None
-    if world > 1:
+    if world > 1 and ex is not None:
         ts = []
         for i in range(4):
             flush.zero_()
@@ -348,6 +357,8 @@ def run_b200(args):
         tree = step()
         torch.cuda.synchronize()
         root = tree.root.clone()
+    if world > 1 and ex is None:
+        other_ms = None
 
     # ---- parity of the timed result: the root against the oracle's committed root (every rank holds the root)
     g = gold.get(args.workload, {})
@@ -377,6 +388,13 @@ def run_b200(args):
     h_top = torch.empty((max(world - 1, 1), 4), dtype=torch.int64, pin_memory=True)
 
     def e2e_call(hl, hln, hn):
+        if world > 1 and ex is None:
+            N.check(N.lib.cpb_merkle_poseidon_build(ctx, ctx, N.C.cast(hl.data_ptr(), N.u64p), leaf_len, n_local,
+                                                    N.C.cast(hln.data_ptr(), N.u64p), N.C.cast(hn.data_ptr(), N.u64p)))
+            r = hn[0].to(dev, non_blocking=False).reshape(1, 4)
+            roots = torch.empty((world, 4), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(roots, r)
+            return backend.from_digests(roots)[0].cpu()
         if world > 1:       # this rank's shard through the host-pointer sharded call: copies, hashing, root exchange, top levels
             N.check(N.lib.cpb_merkle_poseidon_build_sharded(ctx, ctx, ex.handle, N.C.cast(hl.data_ptr(), N.u64p), leaf_len, n_local,
                                                             N.C.cast(hln.data_ptr(), N.u64p), N.C.cast(hn.data_ptr(), N.u64p),
@@ -479,7 +497,7 @@ def run_b200(args):
                            "parallelism": (f"leaf-sharded x{world}; subtree roots exchanged " +
                                            ("inside each rank's last kernel over NVLink peer memory (CUDA IPC), top levels fused in" if use_fused
                                             else "by one NCCL all-gather (torch.distributed)")) if world > 1 else "one GPU",
-                           "other_exchange_ms_per_step": other_ms, "other_exchange": None if world == 1 else ("nccl all-gather" if use_fused else "fused peer-memory kernel"),
+                           "other_exchange_ms_per_step": other_ms, "exchange_error": ex_error, "other_exchange": None if world == 1 else ("nccl all-gather" if use_fused else "fused peer-memory kernel"),
                            "l2": "flushed (256 MB write) between timed steps",
                            "perms_per_step": perms_total, "inputs": "SplitMix64 stream over the global leaf index (bench_inputs.py): identical tree at every N"},
                 "root": root_u, "root_matches_oracle": root_ok, "slices_match_single_gpu_build": slices_ok,
@@ -487,7 +505,7 @@ def run_b200(args):
                 "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
                 "e2e": {"value": e2e_value, "unit": "perms/s", "h2d_bytes_per_step": n_local * leaf_len * 32 * world,
                         "d2h_bytes_per_step": (2 * n_local - 1) * 32 * world, "steps": e2e_steps, "root_matches_oracle": e2e_root_ok,
-                        "api": "cpb_merkle_poseidon_build (host pointers, pinned)" if world == 1 else "cpb_merkle_poseidon_build_sharded (host pointers, pinned; root exchange inside)",
+                        "api": "cpb_merkle_poseidon_build (host pointers, pinned)" if (world == 1 or ex is None) else "cpb_merkle_poseidon_build_sharded (host pointers, pinned; root exchange inside)",
                         "pageable": e2e_pageable},
                 "roofline": roofline, "integer_pipe": integer, "configs": configs, "configs_clocks": cfg_clocks}
         if world == 1:

@@ -121,3 +121,20 @@ def test_generic_config_level_loop_heap_order():
     import pytest
     with pytest.raises(ValueError):
         Toy().build_from_digests(None, ln[:6], 0)
+
+
+def test_multi_gpu_entry_points_validate_their_arguments():
+    """cpb_exchange_* / cpb_multi_* reject bad shapes before touching a device (include/cpb200.h, "Merkle tree across
+    several GPUs"); CPB_NCCL_ERROR is part of the status enum a shim must map."""
+    h = N.vp()
+    for world, rank in ((3, 0), (0, 0), (4, 4), (2, -1), (32, 0)):
+        assert N.lib.cpb_exchange_create(0, world, rank, C.byref(h)) == N.CPB_BAD_PARAMS
+    devs = (C.c_int * 3)(0, 1, 2)
+    assert N.lib.cpb_multi_create(3, devs, C.byref(h)) == N.CPB_BAD_PARAMS           # not a power of two
+    dup = (C.c_int * 2)(0, 0)
+    assert N.lib.cpb_multi_create(2, dup, C.byref(h)) == N.CPB_BAD_PARAMS            # the same device twice
+    assert N.lib.cpb_multi_create(2, None, C.byref(h)) == N.CPB_NULL_POINTER
+    assert N.lib.cpb_merkle_poseidon_build_multi(None, None, None, None, 2, 4, None, None) == N.CPB_NULL_POINTER
+    assert N.lib.cpb_exchange_world(None) == 0 and N.lib.cpb_exchange_rank(None) == -1 and N.lib.cpb_multi_uses_nccl(None) == 0
+    assert N.CPB_NCCL_ERROR == 9
+    assert N.lib.cpb_host_register(None, 16) == N.CPB_NULL_POINTER
