@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, os.environ.get("CPB_LIB_NAME", "libcpb200.so"))   # CPB_LIB_NAME: development variants only
 
 u64p = C.POINTER(C.c_uint64)
+szp = C.POINTER(C.c_size_t)
 u8p = C.POINTER(C.c_uint8)
 vp = C.c_void_p
 
@@ -84,6 +85,22 @@ SIGNATURES = {
     "cpb_merkle_poseidon_build_sharded": (C.c_int, [vp, vp, vp, u64p, C.c_size_t, C.c_size_t, u64p, u64p, u64p]),
     "cpb_merkle_poseidon_from_digests_sharded_dev": (C.c_int, [vp, vp, vp, C.c_size_t, vp, vp, vp]),
     "cpb_merkle_mixed_build_sharded_dev": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, vp, vp]),
+    "cpb_field_serialized_size": (C.c_size_t, [C.c_int]),
+    "cpb_field_serialize": (C.c_int, [C.c_int, u64p, C.c_size_t, u8p]),
+    "cpb_field_deserialize": (C.c_int, [C.c_int, u8p, C.c_size_t, u64p]),
+    "cpb_point_serialized_size": (C.c_size_t, [C.c_int, C.c_int]),
+    "cpb_point_serialize": (C.c_int, [C.c_int, u64p, C.c_size_t, C.c_int, u8p]),
+    "cpb_point_deserialize": (C.c_int, [C.c_int, u8p, C.c_size_t, C.c_int, C.c_int, u64p]),
+    "cpb_poseidon_config_serialize": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, u64p, u64p, u8p, C.c_size_t, szp]),
+    "cpb_poseidon_config_deserialize": (C.c_int, [C.c_int, u8p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                                  C.POINTER(C.c_int), u64p, u64p, C.c_size_t, u64p, C.c_size_t]),
+    "cpb_pedersen_parameters_serialize": (C.c_int, [C.c_int, C.c_int, C.c_int, u64p, C.c_int, u8p, C.c_size_t, szp]),
+    "cpb_pedersen_parameters_deserialize": (C.c_int, [C.c_int, u8p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), u64p, C.c_size_t]),
+    "cpb_path_serialize": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, u64p, u64p, C.c_size_t, C.c_uint64, u8p, C.c_size_t, szp]),
+    "cpb_path_deserialize": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_size_t, u64p, u64p, C.c_size_t, szp, u64p]),
+    "cpb_multipath_serialize": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, u64p, u64p, u64p, u64p, u64p, u8p, C.c_size_t, szp]),
+    "cpb_multipath_deserialize": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_size_t, szp, szp, u64p, u64p, u64p, u64p, u64p,
+                                            C.c_size_t, C.c_size_t]),
     "cpb_multi_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]),
     "cpb_multi_destroy": (None, [vp]),
     "cpb_multi_uses_nccl": (C.c_int, [vp]),

@@ -76,7 +76,7 @@ typedef struct cpb_multi cpb_multi;         /* a group of GPUs driven by one pro
 
 const char* cpb_last_error(void);
 
-/* ABI revision of this header: bumped when entry points or status codes are added (2 = CPB_INTERNAL_ERROR, cpb_abi_version; 3 = _dev field conversion, host pinning, launch count, multi-GPU build, CPB_NCCL_ERROR). */
+/* ABI revision of this header: bumped when entry points or status codes are added (2 = CPB_INTERNAL_ERROR, cpb_abi_version; 3 = _dev field conversion, host pinning, launch count, multi-GPU build, CPB_NCCL_ERROR, wire formats). */
 #define CPB_ABI_VERSION 3
 int cpb_abi_version(void);
 int cpb_version(void);
@@ -322,6 +322,50 @@ int cpb_multi_uses_nccl(const cpb_multi* m);
 cpb_status cpb_merkle_poseidon_build_multi(cpb_multi* m, cpb_poseidon_ctx* const* leaf_ctxs, cpb_poseidon_ctx* const* node_ctxs,
                                            const uint64_t* leaves, size_t leaf_len, size_t n, uint64_t* leaf_nodes,
                                            uint64_t* non_leaf_nodes);
+
+/* ---- wire formats --------------------------------------------------------------------------------- */
+/* `CanonicalSerialize` / `CanonicalDeserialize` images of the types that cross the boundary (derives at
+ * R/sponge/poseidon/mod.rs:25, R/crh/pedersen/mod.rs:28, R/merkle_tree/mod.rs:139,239), for hosts that exchange parameters
+ * or proofs with an arkworks process as bytes (a Rust host serialises with ark-serialize itself).  Host code, no GPU.
+ * Leaf encodings are ark-serialize / ark-ff / ark-ec 0.4 conventions (dependencies of the reference, not vendored;
+ * restated, not pinned by reference vectors): u64/usize = 8 bytes LE; Vec<T> = u64 length + elements; Fp = ceil(bits/8)
+ * bytes LE of the canonical value; twisted-Edwards affine point compressed = y with bit 7 of the last byte set when x > -x,
+ * uncompressed = x || y.  Errors: CPB_BAD_LENGTH = unexpected end / trailing bytes / output buffer too small,
+ * CPB_BAD_PARAMS = "invalid data" (unreduced element, not a curve point, not in the prime-order subgroup when `validate`).
+ * Serialisers write `*written`; with out == NULL they only report the size. */
+size_t cpb_field_serialized_size(int field_id);
+cpb_status cpb_field_serialize(int field_id, const uint64_t* mont, size_t n, uint8_t* out);
+cpb_status cpb_field_deserialize(int field_id, const uint8_t* in, size_t n, uint64_t* mont_out);
+size_t cpb_point_serialized_size(int curve_id, int compress);
+cpb_status cpb_point_serialize(int curve_id, const uint64_t* xy, size_t n, int compress, uint8_t* out);
+cpb_status cpb_point_deserialize(int curve_id, const uint8_t* in, size_t n, int compress, int validate, uint64_t* xy_out);
+/* PoseidonConfig{full_rounds, partial_rounds, alpha, ark, mds, rate, capacity} (R/sponge/poseidon/mod.rs:26-45). */
+cpb_status cpb_poseidon_config_serialize(int field_id, int rate, int capacity, int full_rounds, int partial_rounds, uint64_t alpha,
+                                         const uint64_t* ark, const uint64_t* mds, uint8_t* out, size_t out_cap, size_t* written);
+/* ark_out / mds_out may be NULL: the shape outputs alone (first pass), then a second call with buffers. */
+cpb_status cpb_poseidon_config_deserialize(int field_id, const uint8_t* in, size_t len, int* rate, int* capacity, int* full_rounds,
+                                           int* partial_rounds, uint64_t* alpha, uint64_t* ark_out, size_t ark_cap_elems,
+                                           uint64_t* mds_out, size_t mds_cap_elems);
+/* crh::pedersen::Parameters{generators: Vec<Vec<C>>} (R/crh/pedersen/mod.rs:28-31); points as affine. */
+cpb_status cpb_pedersen_parameters_serialize(int curve_id, int window_size, int num_windows, const uint64_t* generators_xy, int compress,
+                                             uint8_t* out, size_t out_cap, size_t* written);
+cpb_status cpb_pedersen_parameters_deserialize(int curve_id, const uint8_t* in, size_t len, int compress, int validate, int* window_size,
+                                               int* num_windows, uint64_t* generators_xy_out, size_t cap_points);
+/* merkle_tree::Path (R/merkle_tree/mod.rs:139-152) and MultiPath (:239-254).  Digest kinds: 0 = field element (id = cpb_field),
+ * 1 = compressed / 2 = uncompressed affine point (id = cpb_curve); leaf and inner digests may differ (Config::LeafDigest /
+ * InnerDigest).  MultiPath is passed flattened: n paths, suffix_lengths[n], `suffixes` = the suffix digests back to back. */
+cpb_status cpb_path_serialize(int leaf_kind, int leaf_id, int inner_kind, int inner_id, const uint64_t* leaf_sibling_hash,
+                              const uint64_t* auth_path, size_t path_len, uint64_t leaf_index, uint8_t* out, size_t out_cap, size_t* written);
+cpb_status cpb_path_deserialize(int leaf_kind, int leaf_id, int inner_kind, int inner_id, int validate, const uint8_t* in, size_t len,
+                                uint64_t* leaf_sibling_hash, uint64_t* auth_path, size_t path_cap, size_t* path_len, uint64_t* leaf_index);
+cpb_status cpb_multipath_serialize(int leaf_kind, int leaf_id, int inner_kind, int inner_id, size_t n, const uint64_t* leaf_siblings_hashes,
+                                   const uint64_t* prefix_lengths, const uint64_t* suffix_lengths, const uint64_t* suffixes,
+                                   const uint64_t* leaf_indexes, uint8_t* out, size_t out_cap, size_t* written);
+/* With leaf_siblings_hashes == NULL only *n_paths and *n_suffix_digests are written (size query). */
+cpb_status cpb_multipath_deserialize(int leaf_kind, int leaf_id, int inner_kind, int inner_id, int validate, const uint8_t* in, size_t len,
+                                     size_t* n_paths, size_t* n_suffix_digests, uint64_t* leaf_siblings_hashes, uint64_t* prefix_lengths,
+                                     uint64_t* suffix_lengths, uint64_t* suffixes, uint64_t* leaf_indexes, size_t cap_paths,
+                                     size_t cap_suffix_digests);
 
 #ifdef __cplusplus
 }

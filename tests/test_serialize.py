@@ -86,3 +86,35 @@ def test_path_and_multipath_round_trip():
     P = J.random_point(OF.SplitMix64(5))
     pp = Path(J.base_field.elements(list(P)), [J.base_field.elements(list(J.double(P)))], 1)
     assert np.array_equal(S.de_path(S.ser_path(pp, pc), pc).auth_path[0], pp.auth_path[0])
+
+
+def test_c_encoders_equal_an_independent_python_restatement():
+    """The library's encoders (csrc/cpb_serialize.cu through the C-ABI) against oracle/wire.py, byte for byte: PoseidonConfig, a
+    real Merkle path / multiproof shape with field digests, points with both signs in both encodings."""
+    from helpers import oracle_config
+    from oracle import jubjub as jj, merkle as OM, wire as W
+    _, ocfg = oracle_config("bls_default_r2")
+    cfg = product_config("bls_default_r2")
+    assert S.ser_poseidon_config(cfg) == W.poseidon_config(ocfg)
+    p = ocfg.p
+    rng = OF.SplitMix64(77)
+    digests = [rng.field(p) for _ in range(16)]
+    two = lambda l, r: (l * 3 + r * 5 + 1) % p                          # noqa: E731  any deterministic stand-in: layout test only
+    t = OM.MerkleTree(digests, two, two)
+    enc = lambda v: W.fe(v, p)                                          # noqa: E731
+    codec = S.FieldDigest(F)
+    for i in (0, 7, 15):
+        sib, auth, idx = t.generate_proof(i)
+        gp = Path(F.elements([sib])[0], [F.elements([a])[0] for a in auth], idx)
+        assert S.ser_path(gp, codec) == W.path(sib, auth, idx, enc)
+    sibs, prefix, suffixes, idx = t.generate_multi_proof([1, 2, 3, 9, 15])
+    gm = MultiPath([F.elements([s])[0] for s in sibs], prefix, [[F.elements([a])[0] for a in suf] for suf in suffixes], idx)
+    assert S.ser_multipath(gm, codec) == W.multipath(sibs, prefix, suffixes, idx, enc)
+    back = S.de_multipath(S.ser_multipath(gm, codec), codec)
+    assert back.auth_paths_prefix_lenghts == prefix and back.leaf_indexes == idx
+    assert [[F.to_ints(a)[0] for a in suf] for suf in back.auth_paths_suffixes] == [list(s) for s in suffixes]
+    for k in range(6):
+        P = jj.mul(jj.COFACTOR, jj.point_from_y(rng.field(jj.Q)) or jj.IDENTITY)
+        for pt in (P, ((-P[0]) % jj.Q, P[1])):
+            for compress in (True, False):
+                assert S.ser_point(J, J.base_field.elements(list(pt)), compress) == W.te_point(pt, jj.Q, compress)
