@@ -10,9 +10,9 @@
 //                               phase 2: lane w forms row w of the matrix as one lazy dot product   (~2 products)
 //   sparse partial round k      x = lane 0, alpha = e + 1:
 //                               phase 1: warp 0: y = x^e  (for alpha = 2^k + 1: k squarings)
-//                                        warp j = 1, 2: t_j = v_j * x,  u_j = w^_j * s_j         (x published by warp 0 earlier)
-//                                        warp 3: a = m00 * x
-//                               phase 2: warp 0: lane 0 <- a * y + u_1 + u_2 (+ constant)          = m00 * x^alpha + sum w^_j s_j
+//                                        warp j = 1, 2: u_j = w^_j * s_j, then t_j = v_j * x       (x published by warp 0 earlier)
+//                                        warp 3: a = m00 * x, then u = u_1 + u_2 (+ constant)      (named barrier with warps 1, 2)
+//                               phase 2: warp 0: lane 0 <- a * y + u                               = m00 * x^alpha + sum w^_j s_j
 //                                        warp j: s_j <- s_j + t_j * y                               = s_j + v_j * x^alpha
 //
 // i.e. the S-box's last product is merged with the multiplication by m00 and by v_j -- (m00 * x) * x^e == m00 * x^alpha
@@ -29,10 +29,22 @@
 namespace cpb {
 
 // exchange slots, each [32 hashes] x 8 words: lanes 0..2 of the state (full rounds), then x, y, a, u1, u2 (partial rounds)
-enum { TS_L0 = 0, TS_L1 = 1, TS_L2 = 2, TS_X = 3, TS_Y = 4, TS_A = 5, TS_U1 = 6, TS_U2 = 7, TS_COUNT = 8 };
+enum { TS_L0 = 0, TS_L1 = 1, TS_L2 = 2, TS_X = 3, TS_Y = 4, TS_A = 5, TS_U1 = 6, TS_U2 = 7, TS_U = 8, TS_COUNT = 9 };
 CPB_HD u32* team_slot(u32* xb, int slot, int lane) { return xb + ((slot * 32 + lane) * 8); }
 constexpr int kTeamXbWords = TS_COUNT * 32 * 8;
 constexpr int kTeamThreads = 128;
+
+// Named barrier among the three helper warps (1, 2, 3) inside phase 1 of a sparse partial round: warps 1, 2 arrive after
+// publishing u_j, warp 3 after publishing a; warp 3 then sums u_1 + u_2 (+ constant) while warps 1, 2 go on with t_j, so that
+// warp 0 needs one product and ONE addition in phase 2 (-2.5 % per level).  On the host (sequential model: w = 0, 1, 2, 3 in
+// order) it is a no-op.  Four warps = one per scheduler is the sweet spot: a variant with two more helper warps (t_j = v_j * x
+// off warps 1, 2) measured 5 % SLOWER -- a second active warp on the critical warp's scheduler competes for its multiplier
+// pipe, which is what bounds a lone warp.
+#if defined(__CUDA_ARCH__)
+#define CPB_TEAM_HELPER_BARRIER() asm volatile("bar.sync 1, 96;" ::: "memory")
+#else
+#define CPB_TEAM_HELPER_BARRIER() ((void)0)
+#endif
 
 struct TeamRound {
     bool full, sparse_partial;
@@ -83,19 +95,29 @@ CPB_HD void team_phase1(u32* s, u32* t, int w, int lane, int r, const PoseidonDe
         team_pow<F>(y, P.alpha - 1, top_bit_e, pm);             // x^(alpha-1); s keeps x (not needed afterwards)
         st_elem(team_slot(xb, TS_Y, lane), y);
     } else if (w == 3) {
-        u32 x[8], a[8];
+        u32 x[8], a[8], u1[8], u2[8];
         ld_elem(x, team_slot(xb, TS_X, lane));
         ld_elem(c, row);
         fp_mul<F>(a, x, c, pm);
         st_elem(team_slot(xb, TS_A, lane), a);
+        CPB_TEAM_HELPER_BARRIER();                              // u_1, u_2 are published
+        ld_elem(u1, team_slot(xb, TS_U1, lane));
+        ld_elem(u2, team_slot(xb, TS_U2, lane));
+        fp_add<F>(u1, u1, u2);
+        if (R.k + 1 < P.rp) {                                   // the lane-0 constant of the next round rides along
+            ld_elem(c, cs + 8 * (P.off_pc + R.k + 1));
+            fp_add<F>(u1, u1, c);
+        }
+        st_elem(team_slot(xb, TS_U, lane), u1);
     } else {
         u32 x[8], u[8];
+        ld_elem(c, row + 8 * w);
+        fp_mul<F>(u, s, c, pm);                                 // w^_j * s_j: needs nothing from this round, goes first
+        st_elem(team_slot(xb, TS_U1 + (w - 1), lane), u);
+        CPB_TEAM_HELPER_BARRIER();
         ld_elem(x, team_slot(xb, TS_X, lane));
         ld_elem(c, row + 8 * (3 + (w - 1)));
         fp_mul<F>(t, x, c, pm);                                 // v_j * x
-        ld_elem(c, row + 8 * w);
-        fp_mul<F>(u, s, c, pm);                                 // w^_j * s_j
-        st_elem(team_slot(xb, TS_U1 + (w - 1), lane), u);
     }
 }
 
@@ -115,20 +137,13 @@ CPB_HD void team_phase2(u32* s, const u32* t, int w, int lane, int r, const Pose
         return;
     }
     if (w == 0) {
-        u32 a[8], y[8], u1[8], u2[8], d[8];
+        u32 a[8], y[8], u[8], d[8];
         ld_elem(a, team_slot(xb, TS_A, lane));
         ld_elem(y, team_slot(xb, TS_Y, lane));
-        ld_elem(u1, team_slot(xb, TS_U1, lane));
-        ld_elem(u2, team_slot(xb, TS_U2, lane));
+        ld_elem(u, team_slot(xb, TS_U, lane));                  // u_1 + u_2 (+ next constant), summed by warp 3
         fp_mul<F>(d, a, y, pm);
-        fp_add<F>(d, d, u1);
-        fp_add<F>(d, d, u2);
-        if (R.k + 1 < P.rp) {
-            ld_elem(c, cs + 8 * (P.off_pc + R.k + 1));
-            fp_add<F>(s, d, c);
-        } else {
-            fp_copy(s, d);
-        }
+        fp_add<F>(s, d, u);
+        (void)c;
     } else if (w < 3) {
         u32 y[8], tmp[8];
         ld_elem(y, team_slot(xb, TS_Y, lane));
