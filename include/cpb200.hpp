@@ -187,6 +187,59 @@ public:
         }
         return std::vector<Fe>(path.rbegin(), path.rend());
     }
+    Fe leaf_sibling_hash(size_t index) const { return leaf_nodes[index ^ 1]; }
+
+    // n x Path::verify (mod.rs:172-212) against `root` in ONE kernel launch: proofs for leaves `indexes` of this tree
+    // (generate_proof for each), `leaves` = the claimed leaves, leaf_len elements each.  ok[i] = 1 when path i recomputes the root.
+    std::vector<uint8_t> verify_batch(const poseidon::Config& leaf, const poseidon::Config& two_to_one, const Fe& root,
+                                      const std::vector<size_t>& indexes, const std::vector<Fe>& leaves, size_t leaf_len) const {
+        const size_t n = indexes.size(), plen = height() - 2;
+        std::vector<Fe> sib(n), paths(n * plen);
+        std::vector<uint64_t> idx(n);
+        for (size_t i = 0; i < n; i++) {
+            sib[i] = leaf_sibling_hash(indexes[i]);
+            std::vector<Fe> ap = auth_path(indexes[i]);
+            for (size_t k = 0; k < plen; k++) paths[i * plen + k] = ap[k];
+            idx[i] = indexes[i];
+        }
+        std::vector<uint8_t> ok(n, 0);
+        if (n)
+            check(cpb_merkle_poseidon_verify_batch(leaf.ctx(), two_to_one.ctx(), root.data(), leaves[0].data(), leaf_len, sib[0].data(),
+                                                   plen ? paths[0].data() : nullptr, plen, idx.data(), ok.data(), n));
+        return ok;
+    }
+};
+
+// A group of GPUs driven by this process (include/cpb200.h, "Merkle tree across several GPUs"): MerkleTree::new with the
+// leaves sharded over the devices; the result is the reference's two arrays, identical to a one-GPU build.
+class GpuGroup {
+public:
+    explicit GpuGroup(const std::vector<int>& devices) : devices_(devices) {
+        cpb_multi* m = nullptr;
+        check(cpb_multi_create((int)devices.size(), devices.data(), &m));
+        m_.reset(m, cpb_multi_destroy);
+    }
+    bool uses_nccl() const { return cpb_multi_uses_nccl(m_.get()) != 0; }
+    // leaf[d] / two_to_one[d]: the same parameters, created on devices()[d] (Config's `device` argument)
+    PoseidonMerkleTree create(const std::vector<const poseidon::Config*>& leaf, const std::vector<const poseidon::Config*>& two_to_one,
+                              const std::vector<Fe>& leaves, size_t leaf_len) const {
+        if (leaf.size() != devices_.size() || two_to_one.size() != devices_.size()) throw Error(CPB_BAD_PARAMS, "one context per device");
+        std::vector<cpb_poseidon_ctx*> lc, nc;
+        for (auto* c : leaf) lc.push_back(c->ctx());
+        for (auto* c : two_to_one) nc.push_back(c->ctx());
+        PoseidonMerkleTree t;
+        const size_t n = leaf_len ? leaves.size() / leaf_len : 0;
+        t.leaf_nodes.resize(n);
+        t.non_leaf_nodes.resize(n ? n - 1 : 0);
+        check(cpb_merkle_poseidon_build_multi(m_.get(), lc.data(), nc.data(), leaves.empty() ? nullptr : leaves[0].data(), leaf_len, n,
+                                              n ? t.leaf_nodes[0].data() : nullptr, n > 1 ? t.non_leaf_nodes[0].data() : nullptr));
+        return t;
+    }
+    const std::vector<int>& devices() const { return devices_; }
+
+private:
+    std::vector<int> devices_;
+    std::shared_ptr<cpb_multi> m_;
 };
 
 }  // namespace cpb

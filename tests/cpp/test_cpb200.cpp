@@ -51,6 +51,15 @@ int main() {
     REQUIRE(tree.auth_path(5).size() == tree.height() - 2);
     REQUIRE(tree.auth_path(5)[0] == tree.non_leaf_nodes[1]);                                // sibling of the subtree holding leaf 5
 
+    // all 8 paths verified in one launch; a tampered leaf is the only one rejected (Path::verify, mod.rs:172-212)
+    std::vector<size_t> all = {0, 1, 2, 3, 4, 5, 6, 7};
+    std::vector<uint8_t> ok = tree.verify_batch(*params, *params, tree.root(), all, leaves, 2);
+    for (uint8_t v : ok) REQUIRE(v == 1);
+    std::vector<Fe> tampered = leaves;
+    tampered[2 * 3][0] ^= 1;
+    ok = tree.verify_batch(*params, *params, tree.root(), all, tampered, 2);
+    for (size_t i = 0; i < 8; i++) REQUIRE(ok[i] == (i == 3 ? 0 : 1));
+
     bool threw = false;
     try { PoseidonMerkleTree::create(*params, *params, std::vector<Fe>(leaves.begin(), leaves.begin() + 6), 2); }   // 3 leaves
     catch (const Error& e) { threw = e.status == CPB_NOT_POW2; }
