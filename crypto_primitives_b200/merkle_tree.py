@@ -376,19 +376,21 @@ class MerkleTree:
         return Path(self.get_leaf_sibling_hash(index), self._compute_auth_path(index), index)
 
     def generate_multi_proof(self, indexes) -> MultiPath:
-        """mod.rs:589-623."""
+        """mod.rs:589-623: sorted, de-duplicated indexes; every auth path is stored as the length of the prefix it shares with
+        the previous one plus its own suffix.  The paths come from the vectorised index arithmetic of generate_proofs_batch;
+        the shared-prefix lengths are one array comparison."""
         idx = sorted(set(int(i) for i in indexes))
-        prefix, suffixes, sibs, prev = [], [], [], []
-        for i in idx:
-            sibs.append(self.get_leaf_sibling_hash(i))
-            path = self._compute_auth_path(i)
-            k = 0
-            while k < len(prev) and k < len(path) and np.array_equal(prev[k], path[k]):
-                k += 1
-            prefix.append(k)
-            suffixes.append(path[k:])
-            prev = path
-        return MultiPath(sibs, prefix, suffixes, idx)
+        if not idx:
+            return MultiPath([], [], [], [])
+        sib, paths, _ = self.generate_proofs_batch(idx)
+        k, plen = paths.shape[0], paths.shape[1]
+        flat = paths.reshape(k, plen, -1)
+        same = np.all(flat[1:] == flat[:-1], axis=2) if k > 1 else np.zeros((0, plen), dtype=bool)   # (k-1, plen)
+        # length of the common prefix with the previous path = index of the first differing node (plen when all agree)
+        lead = np.where(same.all(axis=1), plen, np.argmin(same, axis=1)) if plen else np.zeros(max(k - 1, 0), dtype=np.int64)
+        prefix = [0] + [int(x) for x in lead]
+        suffixes = [[paths[i, j].copy() for j in range(prefix[i], plen)] for i in range(k)]
+        return MultiPath([sib[i].copy() for i in range(k)], prefix, suffixes, idx)
 
     def generate_proofs_batch(self, indexes):
         """generate_proof (mod.rs:547-575) for many leaves at once as arrays: (leaf_sibling_hashes (k, ...), auth_paths

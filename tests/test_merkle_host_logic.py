@@ -132,3 +132,21 @@ def test_blank_uses_the_default_digest():
     assert t.leaf_nodes.shape == (8, 4) and not t.leaf_nodes.any()
     lvl = CFG.two_to_one_batch(None, np.zeros((4, 2, 4), dtype=np.uint64), 0)
     assert np.array_equal(t.non_leaf_nodes[3:7], lvl)
+
+
+def test_multiproof_encoding_equals_the_oracle_and_the_reference_kat():
+    """generate_multi_proof (vectorised) == the oracle's sequential restatement of mod.rs:589-623, and the prefix lengths of the
+    all-leaves multiproof of an 8-leaf tree are the reference's own [0, 2, 1, 2, 0, 2, 1, 2] (R/merkle_tree/tests/mod.rs:166)."""
+    leaves, tree, otree = build(8, 3)
+    mp = tree.generate_multi_proof(range(8))
+    assert mp.auth_paths_prefix_lenghts == [0, 2, 1, 2, 0, 2, 1, 2]
+    rnd = random.Random(1)
+    leaves, tree, otree = build(64, 4)
+    for trial in range(40):
+        sel = rnd.sample(range(64), rnd.choice([1, 2, 7, 33, 64])) + [5, 5]           # duplicates and disorder are normalised
+        sibs, prefix, suffixes, idx = otree.generate_multi_proof(sel)
+        mp = tree.generate_multi_proof(sel)
+        assert mp.leaf_indexes == idx and mp.auth_paths_prefix_lenghts == prefix
+        assert [tuple(int(v) for v in s) for s in mp.leaf_siblings_hashes] == sibs
+        assert [[tuple(int(v) for v in a) for a in suf] for suf in mp.auth_paths_suffixes] == [list(s) for s in suffixes]
+    assert tree.generate_multi_proof([]).leaf_indexes == []
