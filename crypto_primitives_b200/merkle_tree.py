@@ -384,10 +384,13 @@ class MerkleTree:
             return MultiPath([], [], [], [])
         sib, paths, _ = self.generate_proofs_batch(idx)
         k, plen = paths.shape[0], paths.shape[1]
-        flat = paths.reshape(k, plen, -1)
-        same = np.all(flat[1:] == flat[:-1], axis=2) if k > 1 else np.zeros((0, plen), dtype=bool)   # (k-1, plen)
-        # length of the common prefix with the previous path = index of the first differing node (plen when all agree)
-        lead = np.where(same.all(axis=1), plen, np.argmin(same, axis=1)) if plen else np.zeros(max(k - 1, 0), dtype=np.int64)
+        if plen and k > 1:
+            flat = paths.reshape(k, plen, -1)
+            same = np.all(flat[1:] == flat[:-1], axis=2)                                          # (k-1, plen)
+            # length of the common prefix with the previous path = index of the first differing node (plen when all agree)
+            lead = np.where(same.all(axis=1), plen, np.argmin(same, axis=1))
+        else:                                   # a two-leaf tree has empty auth paths (height 2); one leaf has no predecessor
+            lead = np.zeros(max(k - 1, 0), dtype=np.int64)
         prefix = [0] + [int(x) for x in lead]
         suffixes = [[paths[i, j].copy() for j in range(prefix[i], plen)] for i in range(k)]
         return MultiPath([sib[i].copy() for i in range(k)], prefix, suffixes, idx)

@@ -150,3 +150,13 @@ def test_multiproof_encoding_equals_the_oracle_and_the_reference_kat():
         assert [tuple(int(v) for v in s) for s in mp.leaf_siblings_hashes] == sibs
         assert [[tuple(int(v) for v in a) for a in suf] for suf in mp.auth_paths_suffixes] == [list(s) for s in suffixes]
     assert tree.generate_multi_proof([]).leaf_indexes == []
+    # smallest trees: a two-leaf tree has empty auth paths (height 2), a four-leaf tree one node per path
+    for n in (2, 4):
+        leaves, tree, otree = build(n, 10 + n)
+        for sel in ([0], [1], list(range(n))):
+            sibs, prefix, suffixes, idx = otree.generate_multi_proof(sel)
+            mp = tree.generate_multi_proof(sel)
+            assert mp.leaf_indexes == idx and mp.auth_paths_prefix_lenghts == prefix
+            assert [tuple(int(v) for v in s) for s in mp.leaf_siblings_hashes] == sibs
+            assert [[tuple(int(v) for v in a) for a in suf] for suf in mp.auth_paths_suffixes] == [list(s) for s in suffixes]
+            assert mp.verify(None, None, tree.root(), leaves[idx], config=CFG)
