@@ -135,17 +135,21 @@ def oracle_poseidon(field_key):
     return cfg, cref.Poseidon(cfg)
 
 
-def wide_madds_per_perm(field_key: str, t: int, rf: int, rp: int, alpha: int) -> int:
+def wide_madds_per_perm(field_key: str, t: int, rf: int, rp: int, alpha: int, crh: bool = False) -> int:
     """32x32->64 multiply-adds one permutation needs in the device code (csrc/fp.cuh, poseidon.cuh; sparse partial rounds):
     a product row costs 8 for a*b_i plus `red` for m*p (8; 6 for BLS12-381 Fr, whose p[0] = 1 and p[1] = 2^32-1 turn two
     of them into additions); fp_mul = 8 rows; fp_sqr = 28 cross + 8 diagonal products + 8 reduction rows;
     fp_dot<T> = 8 rows of (8T + red); S-box = floor(log2 alpha) squarings + (popcount(alpha) - 1) products;
     full round = t S-boxes + t dot products, partial round = 1 S-box + 1 dot product + (t-1) column products.
-    (BN254 t=3: 61 896, BLS12-381 t=3: 44 784 -- the IMAD.WIDE counts of the committed ncu opcode mixes.)"""
+    (BN254 t=3: 61 896, BLS12-381 t=3: 44 784 -- the IMAD.WIDE counts of the committed ncu opcode mixes.)
+    crh=True: the one-permutation hash kernels (CRH::evaluate / TwoToOneCRH::compress, poseidon.cuh PermuteHint) do not
+    execute the first S-box of the zero capacity lane (its value is a schedule constant) nor the t-1 last-round rows whose
+    lanes are never read; they are not counted either (61 056 / 43 856)."""
     red = 6 if field_key == "bls" else 8
     mul, sqr, dot = 8 * (8 + red), 36 + 8 * red, 8 * (8 * t + red)
     sbox = (alpha.bit_length() - 1) * sqr + (bin(alpha).count("1") - 1) * mul
-    return rf * (t * sbox + t * dot) + rp * (sbox + dot + (t - 1) * mul)
+    total = rf * (t * sbox + t * dot) + rp * (sbox + dot + (t - 1) * mul)
+    return total - (sbox + (t - 1) * dot if crh else 0)
 
 
 def merkle_launches(ctx, n: int) -> int:
@@ -458,13 +462,13 @@ def run_b200(args):
                 "note": "the path is bound by the integer multiply pipe, not HBM (~6e4 IMAD-class instructions per 96 algorithmic bytes); see integer_pipe"}
     sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
 
-    def integer_pipe(fkey, prm, perms, ms):
-        w = wide_madds_per_perm(fkey, prm.rate + prm.capacity, prm.full_rounds, prm.partial_rounds, prm.alpha)
+    def integer_pipe(fkey, prm, perms, ms, crh=False):
+        w = wide_madds_per_perm(fkey, prm.rate + prm.capacity, prm.full_rounds, prm.partial_rounds, prm.alpha, crh)
         int_peak = 148 * 32 * sm_clock * 1e6            # IMAD.WIDE: 32 lanes/clk/SM (profiles/r2_ubench_imad.txt), x sampled SM clock
         return {"wide_madds_per_perm": w, "achieved_wide_madds_per_s": perms * w / (ms * 1e-3), "peak_wide_madds_per_s": int_peak,
                 "frac": perms * w / (ms * 1e-3) / int_peak, "peak_source": "148 SMs x 32 lanes/clk (measured IMAD.WIDE issue rate) x sampled SM clock"}
 
-    integer = integer_pipe(field_key, params, n_local, k_ms)
+    integer = integer_pipe(field_key, params, n_local, k_ms, crh=True)     # the leaf kernel: one-permutation CRH
 
     # ---- the other BASELINE configurations (each checked against committed oracle results)
     configs = {}

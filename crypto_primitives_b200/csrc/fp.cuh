@@ -404,12 +404,19 @@ template <class F, int K> CPB_HD void reduce9(u32* r) {
     }
 }
 
-// The running value of a T-term dot product stays below (T+1) * p * 2^32.  When (T+1) * p < 2^256 that fits the 9 limbs
-// of (E, O) and the overflow word is dead weight: 5 ALU instructions per row.  True for BN254 Fr (254 bits) up to T = 3,
-// BLS12-377 Fr up to 7, Jubjub Fr up to 15; BLS12-381 Fr (255 bits) needs X from T = 2.
+// The running value of a T-term dot product stays below (T+1) * p * 2^32.  When (T+1) * p <= 2^256 that fits the 9 limbs
+// of (E, O) and the overflow word is dead weight: 5 ALU instructions per row.  Decided on the top limb (p < (p[7]+1) * 2^224):
+// BN254 Fr up to T = 4, BLS12-377 Fr up to 12, Jubjub Fr up to 16; BLS12-381 Fr (p/2^256 = 0.453) needs X from T = 2.
 template <class F, int T> CPB_HD constexpr bool dot_needs_x() {
-    constexpr int slack = 8 * LIMB_BITS - F::BITS;      // (T+1) * p < 2^(8*LIMB_BITS)  <=  T + 1 <= 2^slack
-    return slack < 30 && (T + 1) > (1 << (slack < 30 ? slack : 0));
+    return (u64)(T + 1) * ((u64)F::P(7) + 1) > ((u64)1 << LIMB_BITS);
+}
+// The reduced value is (sum_j a_j*b_j + M*p) / R with M < R and a_j, b_j < p, i.e. below p * (T*p/R + 1): the number of
+// conditional subtractions reduce9 needs is the smallest K with T*p <= (2^(K+1) - 1) * R (again on the top limb).  One pass
+// for BN254 Fr up to T = 5 (three-term rows: 1.57 p), two for BLS12-381 Fr at T = 3 (2.36 p).
+template <class F, int T> CPB_HD constexpr int dot_reduce_passes() {
+    int k = 0;
+    while ((u64)T * ((u64)F::P(7) + 1) > (((u64)2 << k) - 1) * ((u64)1 << LIMB_BITS)) k++;
+    return k;
 }
 
 template <class F, int T, int I> CPB_HD void dot_row(u32* E, u32* O, u32& X, const u32 (&a)[T][8], const u32* b, const u32* pm) {
@@ -450,8 +457,8 @@ template <class F, int T> CPB_HD void fp_dot(u32* r, const u32 (&a)[T][8], const
     for (int i = 1; i < 7; i++) w[i] = addc_cc(ev[i], od[i + 1]);
     w[7] = addc_cc(ev[7], 0);
     w[8] = addc(X, 0);
-    // value < (T+1)*p  <  2^(K+1)*p with K = floor(log2(T))
-    constexpr int K = (T >= 8) ? 3 : (T >= 4) ? 2 : (T >= 2) ? 1 : 0;
+    // value < p * (T*p/R + 1) <= 2^(K+1) * p
+    constexpr int K = detail::dot_reduce_passes<F, T>();
     detail::reduce9<F, K>(w);
 #pragma unroll
     for (int i = 0; i < 8; i++) r[i] = w[i];

@@ -15,7 +15,7 @@ namespace cpb {
 struct PoseidonDev {
     int t, rate, cap, rf, rp, sparse;
     u64 alpha;
-    int off_c, off_m, off_mpre, off_cp0, off_pc, off_sp, off_arkp, off_mod, n_elems;
+    int off_c, off_m, off_mpre, off_cp0, off_pc, off_sp, off_arkp, off_mod, off_sc0, n_elems;
     // Always 0.  Kernels add threadIdx.x * zero to the shared-memory address of every constant so
     // that ptxas keeps multiplier operands in ordinary registers: values loaded from a
     // warp-uniform address are promoted to uniform registers, and a multiply-add with a
@@ -79,7 +79,18 @@ template <class F> CPB_HD void pos_sbox(u32* x, u64 alpha, int top_bit, const u3
 // halves of the full rounds share one body through a two-trip outer loop, so there is still a single
 // instance of the dense round; the partial-round loop has no full/partial selection and no lane
 // rotation, i.e. none of the register shuffles the merged loop pays at its control-flow joins.
-template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const PoseidonDev& P, const u32* cs, const u32* pm) {
+//
+// Two things the sponge knows and a bare permutation does not (PermuteHint): (i) in the first permutation of a fresh sponge the
+// capacity lane 0 is zero, so its first S-box input is the round constant itself and S(c) comes from the schedule (off_sc0);
+// (ii) when the permutation's result is only squeezed (no further permutation), the last round needs just the rows of the lanes
+// that are read -- one of t for CRH::evaluate / TwoToOneCRH::compress.  Both leave every value that is used bit-identical.
+struct PermuteHint {
+    bool lane0_zero;       // state lane 0 is zero on entry
+    int out_lo, out_cnt;   // lanes [out_lo, out_lo + out_cnt) of the result are read; everything else is dead
+};
+template <int T> CPB_HD PermuteHint permute_hint_none() { return PermuteHint{false, 0, T}; }
+
+template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const PoseidonDev& P, const u32* cs, const u32* pm, const PermuteHint& H) {
     const int half = P.rf / 2;
     int top_bit = 0;
     for (int i = 63; i > 0; i--)
@@ -94,9 +105,12 @@ template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const Po
 #pragma unroll 1
         for (int q = 0; q < cnt; q++) {
             pos_add_vec<F, T>(s, cs + 8 * (P.off_c + (phase * half + q) * T));
+            const bool first = H.lane0_zero && phase == 0 && q == 0;
+            const bool last = phase == 1 && q == cnt - 1;
 #pragma unroll 1
             for (int j = 0; j < T; j++) {
-                if (alpha_zero) fp_one<F>(s[0]);
+                if (first && j == 0) ld_elem(s[0], cs + 8 * P.off_sc0);      // S(0 + c) of the schedule
+                else if (alpha_zero) fp_one<F>(s[0]);
                 else pos_sbox<F>(s[0], P.alpha, top_bit, pm);
                 pos_rotl<T>(s);
             }
@@ -104,7 +118,8 @@ template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const Po
 #pragma unroll 1
             for (int i = 0; i < T; i++) {
                 u32 d[8];
-                fp_dot<F, T>(d, s, rows + 8 * T * i, pm);
+                fp_zero(d);
+                if (!last || (i >= H.out_lo && i < H.out_lo + H.out_cnt)) fp_dot<F, T>(d, s, rows + 8 * T * i, pm);
 #pragma unroll
                 for (int k = 0; k + 1 < T; k++) fp_copy(n[k], n[k + 1]);
                 fp_copy(n[T - 1], d);
@@ -164,10 +179,11 @@ template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const Po
     }
 }
 
-template <class F, int T> CPB_HD void pos_permute(u32 (&s)[T][8], const PoseidonDev& P, const u32* cs, const u32* pm) {
+template <class F, int T> CPB_HD void pos_permute(u32 (&s)[T][8], const PoseidonDev& P, const u32* cs, const u32* pm,
+                                                  const PermuteHint& H = PermuteHint{false, 0, T}) {
     if constexpr (CPB_POS_SPLIT_FOR(F)) {
         if (P.sparse) {
-            pos_permute_split<F, T>(s, P, cs, pm);
+            pos_permute_split<F, T>(s, P, cs, pm, H);
             return;
         }
     }
@@ -284,11 +300,13 @@ CPB_HD void pos_sponge(u32* out, long n_out, const u32* in, long len, const Pose
                 }
             }
         }
-        pos_permute<F, T>(s, P, cs, pm);
+        const long q = b - (nblocks - 1);              // squeeze block index (when >= 0)
+        const long left = n_out - q * rate;
+        const int cnt = left > rate ? rate : (int)left;
+        PermuteHint H{b == 0 && cap >= 1, 0, T};
+        if (b == nblocks + nsq - 2) { H.out_lo = cap; H.out_cnt = cnt; }     // nothing follows: only the squeezed lanes are read
+        pos_permute<F, T>(s, P, cs, pm, H);
         if (b >= nblocks - 1) {
-            const long q = b - (nblocks - 1);          // squeeze block index
-            const long left = n_out - q * rate;
-            const int cnt = left > rate ? rate : (int)left;
 #pragma unroll
             for (int i = 0; i < T; i++) {
                 int lane = i - cap;

@@ -129,8 +129,9 @@ struct PoseidonSchedule {
     int off_cp0 = 0;   // t        constant vector added before the first partial round
     int off_pc = 0;    // rp       lane-0 constant added after partial round k-1 (entry k; entry 0 unused)
     int off_sp = 0;    // rp x (2t-1): per round the row [m00, w_hat[1..t-1]] then v[1..t-1]  (sparse)
-    int off_arkp = 0;  // rp x t   original partial-round constants                     (dense)
+    int off_arkp = 0;  // rp x t   original partial-round constants                     (dense schedules only; empty when sparse)
     int off_mod = 0;   // 1        the modulus limbs (plain integer): the kernels load them from here into registers
+    int off_sc0 = 0;   // 1        S(C[0][0]): lane 0 after the first S-box when it entered the permutation as zero (fresh sponge)
     int n_elems = 0;
     std::vector<u64> consts;
 };
@@ -271,11 +272,20 @@ inline PoseidonSchedule derive_schedule(const Field& F, const PoseidonParams& P,
     S.off_cp0 = push(Cp0);
     S.off_pc = push(pc);
     S.off_sp = push(sp);
+    if (sparse) arkp.clear();      // the original partial-round constants are read by the dense form only
     S.off_arkp = push(arkp);
     {
         Fe pm;
         memcpy(pm.l, F.p, 32);
         S.off_mod = push(FeVec(1, pm));
+    }
+    {
+        Fe y = F.one(), b = C.empty() ? F.zero() : C[0];                       // C[0][0]^alpha (alpha = 0: the constant one, as the kernels' S-box)
+        for (u64 e = P.alpha; e; e >>= 1) {
+            if (e & 1) y = F.mul(y, b);
+            b = F.mul(b, b);
+        }
+        S.off_sc0 = push(FeVec(1, y));
     }
     S.n_elems = (int)(S.consts.size() / 4);
     return S;

@@ -85,5 +85,7 @@ def test_bench_multiply_add_model_and_host_info():
     import bench
     assert bench.wide_madds_per_perm("bn254", 3, 8, 57, 5) == 61896
     assert bench.wide_madds_per_perm("bls", 3, 8, 31, 17) == 44784
+    assert bench.wide_madds_per_perm("bn254", 3, 8, 57, 5, crh=True) == 61056      # minus one S-box and two last-round rows
+    assert bench.wide_madds_per_perm("bls", 3, 8, 31, 17, crh=True) == 43856
     info = bench.host_cpu_info()
     assert 1 <= info["threads"] <= info["affinity"]
