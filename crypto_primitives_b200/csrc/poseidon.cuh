@@ -85,10 +85,9 @@ template <class F> CPB_HD void pos_sbox(u32* x, u64 alpha, int top_bit, const u3
 // (ii) when the permutation's result is only squeezed (no further permutation), the last round needs just the rows of the lanes
 // that are read -- one of t for CRH::evaluate / TwoToOneCRH::compress.  Both leave every value that is used bit-identical.
 struct PermuteHint {
-    bool lane0_zero;       // state lane 0 is zero on entry
-    int out_lo, out_cnt;   // lanes [out_lo, out_lo + out_cnt) of the result are read; everything else is dead
+    int lane0_zero;        // != 0: state lane 0 is zero on entry
+    unsigned need;         // bit i set: lane i of the result is read; everything else is dead
 };
-template <int T> CPB_HD PermuteHint permute_hint_none() { return PermuteHint{false, 0, T}; }
 
 template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const PoseidonDev& P, const u32* cs, const u32* pm, const PermuteHint& H) {
     const int half = P.rf / 2;
@@ -105,11 +104,11 @@ template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const Po
 #pragma unroll 1
         for (int q = 0; q < cnt; q++) {
             pos_add_vec<F, T>(s, cs + 8 * (P.off_c + (phase * half + q) * T));
-            const bool first = H.lane0_zero && phase == 0 && q == 0;
-            const bool last = phase == 1 && q == cnt - 1;
+            const int first_j = (H.lane0_zero != 0 && phase == 0 && q == 0) ? 0 : -1;     // the lane whose S-box is the schedule constant
+            const unsigned need = (phase == 1 && q == cnt - 1) ? H.need : ~0u;            // rows of this round that are used
 #pragma unroll 1
             for (int j = 0; j < T; j++) {
-                if (first && j == 0) ld_elem(s[0], cs + 8 * P.off_sc0);      // S(0 + c) of the schedule
+                if (j == first_j) ld_elem(s[0], cs + 8 * P.off_sc0);         // S(0 + c) of the schedule
                 else if (alpha_zero) fp_one<F>(s[0]);
                 else pos_sbox<F>(s[0], P.alpha, top_bit, pm);
                 pos_rotl<T>(s);
@@ -119,7 +118,7 @@ template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const Po
             for (int i = 0; i < T; i++) {
                 u32 d[8];
                 fp_zero(d);
-                if (!last || (i >= H.out_lo && i < H.out_lo + H.out_cnt)) fp_dot<F, T>(d, s, rows + 8 * T * i, pm);
+                if ((need >> i) & 1u) fp_dot<F, T>(d, s, rows + 8 * T * i, pm);
 #pragma unroll
                 for (int k = 0; k + 1 < T; k++) fp_copy(n[k], n[k + 1]);
                 fp_copy(n[T - 1], d);
@@ -180,7 +179,7 @@ template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const Po
 }
 
 template <class F, int T> CPB_HD void pos_permute(u32 (&s)[T][8], const PoseidonDev& P, const u32* cs, const u32* pm,
-                                                  const PermuteHint& H = PermuteHint{false, 0, T}) {
+                                                  const PermuteHint& H = PermuteHint{0, ~0u}) {
     if constexpr (CPB_POS_SPLIT_FOR(F)) {
         if (P.sparse) {
             pos_permute_split<F, T>(s, P, cs, pm, H);
@@ -300,19 +299,38 @@ CPB_HD void pos_sponge(u32* out, long n_out, const u32* in, long len, const Pose
                 }
             }
         }
-        const long q = b - (nblocks - 1);              // squeeze block index (when >= 0)
-        const long left = n_out - q * rate;
-        const int cnt = left > rate ? rate : (int)left;
-        PermuteHint H{b == 0 && cap >= 1, 0, T};
-        if (b == nblocks + nsq - 2) { H.out_lo = cap; H.out_cnt = cnt; }     // nothing follows: only the squeezed lanes are read
-        pos_permute<F, T>(s, P, cs, pm, H);
+        pos_permute<F, T>(s, P, cs, pm);
         if (b >= nblocks - 1) {
+            const long q = b - (nblocks - 1);          // squeeze block index
+            const long left = n_out - q * rate;
+            const int cnt = left > rate ? rate : (int)left;
 #pragma unroll
             for (int i = 0; i < T; i++) {
                 int lane = i - cap;
                 if (lane >= 0 && lane < cnt) st_elem(out + 8 * (q * rate + lane), s[i]);
             }
         }
+    }
+}
+
+// The one-permutation case of pos_sponge (len <= rate, 1 <= n_out <= rate, capacity >= 1) -- every hash of a Merkle build and
+// every CRH::evaluate / TwoToOneCRH::compress of up to `rate` elements -- with the permutation told what the sponge knows
+// (PermuteHint): lane 0 enters as zero, and only lanes cap .. cap+n_out-1 of the result are read.
+template <class F, int T>
+CPB_HD void pos_hash_single(u32* out, int n_out, const u32* in, int len, const PoseidonDev& P, const u32* cs, const u32* pm) {
+    u32 s[T][8];
+    const int cap = P.cap;
+#pragma unroll
+    for (int i = 0; i < T; i++) {
+        const int lane = i - cap;
+        if (lane >= 0 && lane < len) ld_elem(s[i], in + 8 * lane);
+        else fp_zero(s[i]);
+    }
+    pos_permute<F, T>(s, P, cs, pm, PermuteHint{1, ((1u << n_out) - 1u) << cap});
+#pragma unroll
+    for (int i = 0; i < T; i++) {
+        const int lane = i - cap;
+        if (lane >= 0 && lane < n_out) st_elem(out + 8 * lane, s[i]);
     }
 }
 

@@ -18,7 +18,8 @@ constexpr int kBlock = 128;
 #endif
 constexpr int pos_min_blocks(int t) { return t <= 3 ? CPB_POS_MINB3 : t <= 5 ? 3 : 1; }
 
-template <class F, int T>
+// SINGLE: len <= rate, 1 <= n_out <= rate, capacity >= 1 (checked by launch_crh_ft): one permutation per hash, pos_hash_single.
+template <class F, int T, bool SINGLE>
 __global__ void __launch_bounds__(kBlock, pos_min_blocks(T))
 k_poseidon_crh(PoseidonDev P, const u32* __restrict__ consts, const u32* __restrict__ in, u32* __restrict__ out,
                long n, long len, long n_out) {
@@ -30,7 +31,8 @@ k_poseidon_crh(PoseidonDev P, const u32* __restrict__ consts, const u32* __restr
     ld_elem(pm, ct + 8 * P.off_mod);
     const long stride = (long)gridDim.x * blockDim.x;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        pos_sponge<F, T>(out + 8 * n_out * i, n_out, in + 8 * len * i, len, P, ct, pm);
+        if constexpr (SINGLE) pos_hash_single<F, T>(out + 8 * n_out * i, (int)n_out, in + 8 * len * i, (int)len, P, ct, pm);
+        else pos_sponge<F, T>(out + 8 * n_out * i, n_out, in + 8 * len * i, len, P, ct, pm);
     }
 }
 
@@ -109,8 +111,14 @@ template <class F, int T>
 cpb_status launch_crh_ft(cpb_poseidon_ctx* c, const u32* in, size_t len, u32* out, size_t n_out, size_t n, cudaStream_t st) {
     size_t smem = (size_t)c->dev.n_elems * 32;
     int grid = 1;
-    CPB_TRY(grid_for(k_poseidon_crh<F, T>, smem, c->sms, (long)n, grid));
-    k_poseidon_crh<F, T><<<grid, kBlock, smem, st>>>(c->dev, c->d_consts, in, out, (long)n, (long)len, (long)n_out);
+    const bool single = len <= (size_t)c->dev.rate && n_out >= 1 && n_out <= (size_t)c->dev.rate && c->dev.cap >= 1;
+    if (single) {
+        CPB_TRY(grid_for(k_poseidon_crh<F, T, true>, smem, c->sms, (long)n, grid));
+        k_poseidon_crh<F, T, true><<<grid, kBlock, smem, st>>>(c->dev, c->d_consts, in, out, (long)n, (long)len, (long)n_out);
+    } else {
+        CPB_TRY(grid_for(k_poseidon_crh<F, T, false>, smem, c->sms, (long)n, grid));
+        k_poseidon_crh<F, T, false><<<grid, kBlock, smem, st>>>(c->dev, c->d_consts, in, out, (long)n, (long)len, (long)n_out);
+    }
     CPB_CUDA(cudaGetLastError());
     return CPB_OK;
 }

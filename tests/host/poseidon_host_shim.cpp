@@ -20,7 +20,11 @@ template <class F, int T>
 static void run_sponge(const PoseidonDev& D, const u32* cs, const u32* in, long len, long n_out, long n, u32* out) {
     u32 pm[8];
     ld_elem(pm, cs + 8 * D.off_mod);
-    for (long i = 0; i < n; i++) pos_sponge<F, T>(out + 8 * n_out * i, n_out, in + 8 * len * i, len, D, cs, pm);
+    const bool single = len <= D.rate && n_out >= 1 && n_out <= D.rate && D.cap >= 1;      // as launch_crh_ft selects the kernel
+    for (long i = 0; i < n; i++) {
+        if (single) pos_hash_single<F, T>(out + 8 * n_out * i, (int)n_out, in + 8 * len * i, (int)len, D, cs, pm);
+        else pos_sponge<F, T>(out + 8 * n_out * i, n_out, in + 8 * len * i, len, D, cs, pm);
+    }
 }
 template <class F, int T>
 static void run_verify(const PoseidonDev& D, const u32* cs, const u32* root, const u32* leaves, long leaf_len, const u32* sib,
@@ -35,7 +39,11 @@ template <class F, int T>
 static void run(const PoseidonDev& D, const u32* cs, const u32* in, long len, long n, u32* out) {
     u32 pm[8];
     ld_elem(pm, cs + 8 * D.off_mod);
-    for (long i = 0; i < n; i++) pos_crh<F, T>(out + 8 * i, in + 8 * len * i, len, D, cs, pm);
+    const bool single = len <= D.rate && D.cap >= 1;                                       // as launch_crh_ft selects the kernel
+    for (long i = 0; i < n; i++) {
+        if (single) pos_hash_single<F, T>(out + 8 * i, 1, in + 8 * len * i, (int)len, D, cs, pm);
+        else pos_crh<F, T>(out + 8 * i, in + 8 * len * i, len, D, cs, pm);
+    }
 }
 
 template <class F>
