@@ -524,8 +524,8 @@ def run_b200(args):
 # DRAM traffic of k_poseidon_crh from the committed `ncu --set full` captures (dram__bytes_read.sum + dram__bytes_write.sum of a
 # 2^20-hash, len-2 launch), per hash.  Update together with the files named here.
 NCU_TRAFFIC = {
-    "bn254": {"bytes_per_hash": (67.205120e6 + 7.277824e6) / (1 << 20), "source": "profiles/r2_ncu_crh_bn254.txt (2^20-hash launch), scaled per hash"},
-    "bls": {"bytes_per_hash": (67.474944e6 + 8.477952e6) / (1 << 20), "source": "profiles/r2_ncu_crh_bls.txt (2^20-hash launch), scaled per hash"},
+    "bn254": {"bytes_per_hash": (67.246848e6 + 6.766848e6) / (1 << 20), "source": "profiles/r2_ncu_crh_bn254.txt (2^20-hash launch), scaled per hash"},
+    "bls": {"bytes_per_hash": (67.188736e6 + 8.603136e6) / (1 << 20), "source": "profiles/r2_ncu_crh_bls.txt (2^20-hash launch), scaled per hash"},
 }
 
 
