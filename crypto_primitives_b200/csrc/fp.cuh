@@ -25,6 +25,7 @@ namespace cpb {
     }
 
 struct Bls12_381_Fr {
+    static constexpr bool LAZY5 = false;
     static constexpr bool SPLIT_ROUNDS = true;   // Poseidon: partial rounds in a loop of their own (poseidon.cuh)
     static constexpr int P0_POW = 0;          // k > 0: p[0] == 2^32 - 2^k + 1
     static constexpr bool P0_ONE = true;       // p[0] == 1  (then -p^-1 mod 2^32 == -1)
@@ -37,6 +38,7 @@ struct Bls12_381_Fr {
     CPB_FIELD_TABLE(R2, 0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u)
 };
 struct Bn254_Fr {
+    static constexpr bool LAZY5 = true;          // Poseidon alpha = 5 partial rounds keep lane 0 in [0, 2p) (poseidon.cuh; bounds there)
     static constexpr bool SPLIT_ROUNDS = true;   // Poseidon: partial rounds in a loop of their own (poseidon.cuh)
     static constexpr int P0_POW = 0;           // p[0] = 2^32 - 2^28 + 1, but the shift/add form measured slower          // k > 0: p[0] == 2^32 - 2^k + 1
     static constexpr bool P0_ONE = false;       // p[0] == 1  (then -p^-1 mod 2^32 == -1)
@@ -49,6 +51,7 @@ struct Bn254_Fr {
     CPB_FIELD_TABLE(R2, 0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u)
 };
 struct Jubjub_Fr {
+    static constexpr bool LAZY5 = false;
     static constexpr bool SPLIT_ROUNDS = true;   // Poseidon: partial rounds in a loop of their own (poseidon.cuh)
     static constexpr int P0_POW = 0;          // k > 0: p[0] == 2^32 - 2^k + 1
     static constexpr bool P0_ONE = false;       // p[0] == 1  (then -p^-1 mod 2^32 == -1)
@@ -61,6 +64,7 @@ struct Jubjub_Fr {
     CPB_FIELD_TABLE(R2, 0x95e57731u, 0x67719aa4u, 0x9ce3fc26u, 0x51b0cef0u, 0xc026e9a5u, 0x69dab7fau, 0x8d127688u, 0x04f6547bu)
 };
 struct Bls12_377_Fr {
+    static constexpr bool LAZY5 = false;
     static constexpr bool SPLIT_ROUNDS = true;   // Poseidon: partial rounds in a loop of their own (poseidon.cuh)
     static constexpr int P0_POW = 0;          // k > 0: p[0] == 2^32 - 2^k + 1
     static constexpr bool P0_ONE = true;       // p[0] == 1  (then -p^-1 mod 2^32 == -1)
@@ -142,6 +146,14 @@ template <class F> CPB_HD void fp_add(u32* r, const u32* a, const u32* b) {
     for (int i = 1; i < 7; i++) r[i] = addc_cc(a[i], b[i]);
     r[7] = addc(a[7], b[7]);   // a+b < 2p < 2^256
     fp_final_sub<F>(r);
+}
+
+// r = a + b without reduction (callers guarantee a + b < 2^256).
+CPB_HD void fp_add_noreduce(u32* r, const u32* a, const u32* b) {
+    r[0] = add_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r[i] = addc_cc(a[i], b[i]);
+    r[7] = addc(a[7], b[7]);
 }
 
 template <class F> CPB_HD void fp_sub(u32* r, const u32* a, const u32* b) {
@@ -262,7 +274,10 @@ template <class F> CPB_HD void next_row(u32* E, u32* O, const u32* a, u32 bi, co
 }  // namespace detail
 
 // r = a*b/R mod p, fully reduced.  a, b in [0,p).  r may alias a or b.
-template <class F> CPB_HD void fp_mul(u32* r, const u32* a, const u32* b, const u32* pm) {
+// LAZY (fields with slack, see F::LAZY5): the conditional subtraction is skipped and r = (a*b + M*p)/R < p*(a*b/(R*p) + 1) is
+// returned as it is.  Operand ranges of the row accumulators: `a` (the full operand of every row) may be any value with
+// a + p < 2^256 -- the running value stays below a + p --, `b` (scanned limb by limb) any 256-bit value.
+template <class F, bool LAZY = false> CPB_HD void fp_mul(u32* r, const u32* a, const u32* b, const u32* pm) {
     u32 ev[8], od[8];
     detail::first_row<F>(ev, od, a, b[0], pm);
     detail::next_row<F>(od, ev, a, b[1], pm);
@@ -277,10 +292,10 @@ template <class F> CPB_HD void fp_mul(u32* r, const u32* a, const u32* b, const 
 #pragma unroll
     for (int i = 1; i < 7; i++) r[i] = addc_cc(ev[i], od[i + 1]);
     r[7] = addc(ev[7], 0);
-    fp_final_sub<F>(r);
+    if (!LAZY) fp_final_sub<F>(r);
 }
 
-template <class F> CPB_HD void fp_sqr(u32* r, const u32* a, const u32* pm);
+template <class F, bool LAZY = false> CPB_HD void fp_sqr(u32* r, const u32* a, const u32* pm);
 
 // ---------------------------------------------------------------------------------------
 // Lazy dot product: r = (sum_j a_j * b_j) / R mod p with ONE Montgomery reduction.
@@ -419,8 +434,8 @@ template <class F, int T> CPB_HD constexpr int dot_reduce_passes() {
     return k;
 }
 
-template <class F, int T, int I> CPB_HD void dot_row(u32* E, u32* O, u32& X, const u32 (&a)[T][8], const u32* b, const u32* pm) {
-    constexpr bool WX = dot_needs_x<F, T>();
+template <class F, int T, int I, int EX> CPB_HD void dot_row(u32* E, u32* O, u32& X, const u32 (&a)[T][8], const u32* b, const u32* pm) {
+    constexpr bool WX = dot_needs_x<F, T + EX>();
     // b: T constants of 8 limbs each (shared memory); this row uses limb I of each
     if (I == 0) {
         u32 bi = b[0];
@@ -441,16 +456,18 @@ template <class F, int T, int I> CPB_HD void dot_row(u32* E, u32* O, u32& X, con
 }  // namespace detail
 
 // r = sum_{j<T} a[j] * b[j] / R mod p, fully reduced.  a[j], b[j] in [0,p).  r must not alias a.
-template <class F, int T> CPB_HD void fp_dot(u32* r, const u32 (&a)[T][8], const u32* b, const u32* pm) {
+// EX > 0: the a[j] may be unreduced as long as sum_j a[j] < (T + EX) * p (outputs of the LAZY multiplier); the overflow word
+// and the number of conditional subtractions are then decided for T + EX terms.
+template <class F, int T, int EX = 0> CPB_HD void fp_dot(u32* r, const u32 (&a)[T][8], const u32* b, const u32* pm) {
     u32 ev[8], od[8], X = 0;
-    detail::dot_row<F, T, 0>(ev, od, X, a, b, pm);
-    detail::dot_row<F, T, 1>(od, ev, X, a, b, pm);
-    detail::dot_row<F, T, 2>(ev, od, X, a, b, pm);
-    detail::dot_row<F, T, 3>(od, ev, X, a, b, pm);
-    detail::dot_row<F, T, 4>(ev, od, X, a, b, pm);
-    detail::dot_row<F, T, 5>(od, ev, X, a, b, pm);
-    detail::dot_row<F, T, 6>(ev, od, X, a, b, pm);
-    detail::dot_row<F, T, 7>(od, ev, X, a, b, pm);
+    detail::dot_row<F, T, 0, EX>(ev, od, X, a, b, pm);
+    detail::dot_row<F, T, 1, EX>(od, ev, X, a, b, pm);
+    detail::dot_row<F, T, 2, EX>(ev, od, X, a, b, pm);
+    detail::dot_row<F, T, 3, EX>(od, ev, X, a, b, pm);
+    detail::dot_row<F, T, 4, EX>(ev, od, X, a, b, pm);
+    detail::dot_row<F, T, 5, EX>(od, ev, X, a, b, pm);
+    detail::dot_row<F, T, 6, EX>(ev, od, X, a, b, pm);
+    detail::dot_row<F, T, 7, EX>(od, ev, X, a, b, pm);
     u32 w[9];
     w[0] = add_cc(ev[0], od[1]);
 #pragma unroll
@@ -458,7 +475,7 @@ template <class F, int T> CPB_HD void fp_dot(u32* r, const u32 (&a)[T][8], const
     w[7] = addc_cc(ev[7], 0);
     w[8] = addc(X, 0);
     // value < p * (T*p/R + 1) <= 2^(K+1) * p
-    constexpr int K = detail::dot_reduce_passes<F, T>();
+    constexpr int K = detail::dot_reduce_passes<F, T + EX>();
     detail::reduce9<F, K>(w);
 #pragma unroll
     for (int i = 0; i < 8; i++) r[i] = w[i];
@@ -469,7 +486,8 @@ template <class F, int T> CPB_HD void fp_dot(u32* r, const u32 (&a)[T][8], const
 // adds (the ALU pipe has slack, the multiply pipe does not), then the 8 diagonal squares are added
 // and the 512-bit value goes through 8 Montgomery reduction rows.  100 wide multiply-adds (84 for
 // BLS12-381 Fr) against 128 (112) for fp_mul(a, a).
-template <class F> CPB_HD void fp_sqr(u32* r, const u32* a, const u32* pm) {
+// LAZY: a < 2^256 with a^2 < R*p; the result (a^2 + M*p)/R < p*(a^2/(R*p) + 1) is returned without the conditional subtraction.
+template <class F, bool LAZY> CPB_HD void fp_sqr(u32* r, const u32* a, const u32* pm) {
     // Cross products a_i*a_j (i<j) sit at limb i+j.  Even positions accumulate in E (index = limb),
     // odd positions in O (index = limb-1), so every product is an aligned 64-bit multiply-add and each
     // row is one carry chain per array.  A chain's carry-out always lands on a limb no earlier row
@@ -562,11 +580,26 @@ template <class F> CPB_HD void fp_sqr(u32* r, const u32* a, const u32* pm) {
     w[0] = add_cc(ev[0], od[1]);
 #pragma unroll
     for (int i = 1; i < 7; i++) w[i] = addc_cc(ev[i], od[i + 1]);
-    w[7] = addc_cc(ev[7], 0);
-    w[8] = addc(X, 0);
-    detail::reduce9<F, 0>(w);          // T < p^2  =>  result < 2p
+    if (LAZY) {                        // result < 2p < 2^256: limb 8 is zero
+        w[7] = addc(ev[7], 0);
+    } else {
+        w[7] = addc_cc(ev[7], 0);
+        w[8] = addc(X, 0);
+        detail::reduce9<F, 0>(w);      // T < p^2  =>  result < 2p
+    }
 #pragma unroll
     for (int i = 0; i < 8; i++) r[i] = w[i];
+}
+
+// Multiplier / squarer whose conditional subtraction is skipped when `lazy` (uniform at run time): one code instance serves
+// both modes in rolled loops.
+template <class F> CPB_HD void fp_mul_rt(u32* r, const u32* a, const u32* b, const u32* pm, bool lazy) {
+    fp_mul<F, true>(r, a, b, pm);
+    if (!lazy) fp_final_sub<F>(r);
+}
+template <class F> CPB_HD void fp_sqr_rt(u32* r, const u32* a, const u32* pm, bool lazy) {
+    fp_sqr<F, true>(r, a, pm);          // a < p: result < 2p either way
+    if (!lazy) fp_final_sub<F>(r);
 }
 
 // x^alpha for the S-box.  5 and 17 get fixed addition chains; anything else falls back to

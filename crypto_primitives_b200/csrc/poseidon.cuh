@@ -46,13 +46,20 @@ template <int T> CPB_HD void pos_rotl(u32 (&s)[T][8]) {
 // x^alpha, left-to-right binary.  For the arkworks S-box exponents (3, 5, 17, 257 = 2^k+1)
 // this is k squarings and one multiplication -- the optimal chain -- from a single pair of
 // inlined multiplier bodies, which keeps the kernel's instruction footprint small.
-template <class F> CPB_HD void pos_sbox(u32* x, u64 alpha, int top_bit, const u32* pm) {
+// lazy (F::LAZY5 fields, alpha = 5, canonical x): the three products skip their conditional subtraction; x^2 < 1.19p, x^4 < 1.27p,
+// x^5 < 1.24p for p/R < 0.19 -- what the dense rows take with EX = 1 (3 * 1.24 p < 4p).
+template <class F> CPB_HD void pos_sbox(u32* x, u64 alpha, int top_bit, const u32* pm, bool lazy = false) {
     u32 x0[8];
     fp_copy(x0, x);
 #pragma unroll 1
     for (int i = top_bit - 1; i >= 0; i--) {
-        fp_sqr<F>(x, x, pm);
-        if ((alpha >> i) & 1) fp_mul<F>(x, x, x0, pm);
+        if constexpr (F::LAZY5) {
+            fp_sqr_rt<F>(x, x, pm, lazy);
+            if ((alpha >> i) & 1) fp_mul_rt<F>(x, x, x0, pm, lazy);
+        } else {
+            fp_sqr<F>(x, x, pm);
+            if ((alpha >> i) & 1) fp_mul<F>(x, x, x0, pm);
+        }
     }
 }
 
@@ -95,6 +102,12 @@ template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const Po
     for (int i = 63; i > 0; i--)
         if ((P.alpha >> i) & 1) { top_bit = i; break; }
     const bool alpha_zero = P.alpha == 0;
+    // Lazy reduction (F::LAZY5: p/2^256 <= 0.19, i.e. BN254 Fr; alpha = 5; widths whose (T+1)-term rows need no overflow word).
+    // Full rounds: the S-box of a canonical x skips its three conditional subtractions (x^5 < 1.24p, see pos_sbox) and the dense
+    // rows take the T unreduced lanes as EX = 1 (T * 1.24p < (T+1)*p for T <= 4), returning canonical values.
+    constexpr bool LZ = F::LAZY5 && !detail::dot_needs_x<F, T + 1>() && T <= 4;
+    static_assert(!F::LAZY5 || 100 * ((u64)F::P(7) + 1) <= 19 * ((u64)1 << LIMB_BITS), "LAZY5 needs p/2^256 <= 0.19");
+    const bool lazy = LZ && CPB_SBOX5 && P.alpha == 5;
     u32 n[T][8];
 #pragma unroll
     for (int i = 0; i < T; i++) fp_zero(n[i]);
@@ -110,7 +123,7 @@ template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const Po
             for (int j = 0; j < T; j++) {
                 if (j == first_j) ld_elem(s[0], cs + 8 * P.off_sc0);         // S(0 + c) of the schedule
                 else if (alpha_zero) fp_one<F>(s[0]);
-                else pos_sbox<F>(s[0], P.alpha, top_bit, pm);
+                else pos_sbox<F>(s[0], P.alpha, top_bit, pm, lazy);
                 pos_rotl<T>(s);
             }
             const u32* rows = cs + 8 * ((phase == 0 && q == half - 1) ? P.off_mpre : P.off_m);
@@ -118,7 +131,7 @@ template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const Po
             for (int i = 0; i < T; i++) {
                 u32 d[8];
                 fp_zero(d);
-                if ((need >> i) & 1u) fp_dot<F, T>(d, s, rows + 8 * T * i, pm);
+                if ((need >> i) & 1u) fp_dot<F, T, LZ ? 1 : 0>(d, s, rows + 8 * T * i, pm);
 #pragma unroll
                 for (int k = 0; k + 1 < T; k++) fp_copy(n[k], n[k + 1]);
                 fp_copy(n[T - 1], d);
@@ -130,20 +143,27 @@ template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const Po
             pos_add_vec<F, T>(s, cs + 8 * P.off_cp0);
             const u32* row = cs + 8 * P.off_sp;
             const u32* pc = cs + 8 * (P.off_pc + 1);
+            // Partial rounds, lazy lane 0: lane 0 lives in [0, 2p) from the constant
+            // addition to the end of the round.  With a, b < 2p the Montgomery product (a*b + M*p)/R is below p*(4p/R + 1) <= 2p,
+            // so x^2, x^4, x^5 need no conditional subtraction, nor does x = d + c (d, c < p).  Consumers: the row product
+            // takes sum_j a_j < (T+1)*p (EX = 1: same code as T canonical terms when (T+2)*p <= 2^256, which is the
+            // condition below) and returns a canonical d; the column products v_j * y are ordinary multiplications whose full
+            // operand y + p stays below 2^256 and whose results are reduced, so lanes 1.. stay canonical.  Saves 4 conditional
+            // subtractions (68 instructions) per partial round; bit-identical outputs.
 #pragma unroll 1
             for (int k = 0; k < P.rp; k++, row += 8 * (2 * T - 1), pc += 8) {
 #if CPB_SBOX5
                 if (P.alpha == 5) {                   // straight-line x^5
                     u32 x2[8];
-                    fp_sqr<F>(x2, s[0], pm);
-                    fp_sqr<F>(x2, x2, pm);
-                    fp_mul<F>(s[0], x2, s[0], pm);
+                    fp_sqr<F, LZ>(x2, s[0], pm);
+                    fp_sqr<F, LZ>(x2, x2, pm);
+                    fp_mul<F, LZ>(s[0], x2, s[0], pm);
                 } else
 #endif
                 if (alpha_zero) fp_one<F>(s[0]);
                 else pos_sbox<F>(s[0], P.alpha, top_bit, pm);
                 u32 d[8];
-                fp_dot<F, T>(d, s, row, pm);
+                fp_dot<F, T, LZ ? 1 : 0>(d, s, row, pm);
                 const u32* v = row + 8 * T;
                 if (T <= CPB_COL_UNROLL_MAX) {
 #pragma unroll
@@ -169,7 +189,8 @@ template <class F, int T> CPB_HD void pos_permute_split(u32 (&s)[T][8], const Po
                 if (k + 1 < P.rp) {
                     u32 c[8];
                     ld_elem(c, pc);
-                    fp_add<F>(s[0], d, c);
+                    if (lazy) fp_add_noreduce(s[0], d, c);
+                    else fp_add<F>(s[0], d, c);
                 } else {
                     fp_copy(s[0], d);
                 }
