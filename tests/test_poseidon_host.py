@@ -202,3 +202,26 @@ def test_odd_full_rounds(shim):
                 rc = shim.host_poseidon_team_compress(fid, rf, rp, C.c_ulonglong(alpha), _P(arkm), _P(mdsm), sp,
                                                       _P(np.ascontiguousarray(pairs)), C.c_long(33), _P(out))
                 assert rc >= 0 and np.array_equal(out, exp), (rf, rp, sp)
+
+
+def test_lazy_reduction_rounds_bn254_alpha5(shim):
+    """BN254 Fr with alpha = 5 runs its rounds with unreduced lane values (poseidon.cuh LZ; bounds in tests/test_lazy_bounds.py):
+    round constants at p-1 (the largest x = d + c), inputs at p-1 / 0 / 1, widths 2 and 3 (the widths LZ admits) and 4 (it does
+    not), many random inputs -- sparse and dense schedules against the oracle."""
+    rnd = random.Random(21)
+    p = OF.BN254_FR
+    for rate, rf, rp in ((2, 8, 57), (1, 8, 56), (3, 8, 56), (2, 2, 1), (2, 3, 2)):
+        t = rate + 1
+        for extreme in (True, False):
+            ark = [[(p - 1 - rnd.randrange(3)) if extreme else rnd.randrange(p) for _ in range(t)] for _ in range(rf + rp)]
+            mds = [[rnd.randrange(p) for _ in range(t)] for _ in range(t)]
+            cfg = OP.PoseidonConfig(p, rf, rp, 5, ark, mds, rate, 1)
+            n = 64 if rp > 10 else 256
+            inp = synth_elems(300 + rate + rf, (n, rate), p)
+            inp[0, :] = cref.ints_to_mont([p - 1] * rate, p)
+            inp[1, :] = cref.ints_to_mont([0] * rate, p)
+            inp[2, :] = cref.ints_to_mont([1] * rate, p)
+            exp = cref.Poseidon(cfg).crh_batch(inp)
+            for sp in (1, 0):
+                rc, out = run(shim, 1, cfg, inp, sp)
+                assert (out == exp).all(), (rate, rf, rp, extreme, sp)
